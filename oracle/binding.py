@@ -1,0 +1,135 @@
+"""ctypes bindings for the checker libraries (TEST INFRASTRUCTURE ONLY).
+
+* ``Oracle``  -> oracle/_build/libdcoracle.so, our plain-C restatement (oracle/dc_oracle.c)
+* ``Ref``     -> oracle/_ref/libdcref.so, the UNMODIFIED reference DCLib/DCIOLib compiled from
+                 /root/reference by oracle/Makefile, driven through oracle/ref_driver.c
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module.  The product package (data_compressor_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libdcoracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libdcref.so")
+REF_CLI = os.path.join(HERE, "_ref", "DCCLI")
+
+# enum dco_stage_id (oracle/dc_oracle.h)
+NORMALIZE, DENORMALIZE, DIFF_ENC, DIFF_DEC, SEG_ENC, SEG_DEC, BAC_ENC, BAC_DEC, LZMH_ENC, LZMH_DEC = range(10)
+
+#: oracle stage id -> (DCCLI encoder name, encode flag)   (DCLib/src/enc_dec.c:51-60)
+STAGE_TO_CLI = {
+    NORMALIZE: ("normalize", 1), DENORMALIZE: ("normalize", 0),
+    DIFF_ENC: ("diff", 1), DIFF_DEC: ("diff", 0),
+    SEG_ENC: ("seg", 1), SEG_DEC: ("seg", 0),
+    BAC_ENC: ("bac", 1), BAC_DEC: ("bac", 0),
+    LZMH_ENC: ("lzmh", 1), LZMH_DEC: ("lzmh", 0),
+}
+
+DEGA_ENC = [NORMALIZE, DIFF_ENC, SEG_ENC, BAC_ENC]
+DEGA_DEC = [BAC_DEC, SEG_DEC, DIFF_DEC, DENORMALIZE]
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checker libraries (building the checker is not using it)."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(buf), dtype=np.uint8)
+    a = np.ascontiguousarray(buf)
+    return a.view(np.uint8).reshape(-1)
+
+
+class Oracle:
+    """Our C restatement.  All results are (code, bytes, nbits)."""
+
+    def __init__(self, path: str = ORACLE_SO):
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.dco_run_chain.restype = C.c_int
+        L.dco_run_chain.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_uint64, C.c_uint, C.c_float,
+                                    C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.dco_dega_encode_batch.restype = C.c_int64
+        L.dco_dega_encode_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_float, C.c_int]
+
+    def run_chain(self, stages, data, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
+        src = _as_u8(data)
+        if nbits is None:
+            nbits = src.size * 8
+        if out_cap is None:
+            out_cap = max(4096, src.size * 24 + 4096)
+        out = np.zeros(out_cap, dtype=np.uint8)
+        out_bits = C.c_uint64(0)
+        st = (C.c_int * len(stages))(*stages)
+        rc = self.lib.dco_run_chain(st, len(stages), src.ctypes.data if src.size else None, nbits, vs, nf,
+                                    int(adaptive), out.ctypes.data, out_cap, C.byref(out_bits))
+        nb = int(out_bits.value)
+        return rc, out[: (nb + 7) // 8].tobytes(), nb
+
+    def dega_encode(self, samples, vs=32, nf=100.0, adaptive=1):
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        return self.run_chain(DEGA_ENC, x, x.size * 32, vs, nf, adaptive)
+
+    def dega_decode(self, payload, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
+        rc, raw, nb = self.run_chain(DEGA_DEC, payload, nbits, vs, nf, adaptive, out_cap=out_cap)
+        return rc, np.frombuffer(raw[: (nb // 32) * 4], dtype=np.float32).copy()
+
+    def dega_encode_batch(self, samples2d, vs=32, nf=100.0, adaptive=1) -> int:
+        x = np.ascontiguousarray(samples2d, dtype=np.float32)
+        assert x.ndim == 2
+        return int(self.lib.dco_dega_encode_batch(x.ctypes.data, x.shape[0], x.shape[1], vs, nf, int(adaptive)))
+
+
+class Ref:
+    """The real reference, in process (not re-entrant: one call at a time per process)."""
+
+    def __init__(self, path: str = REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.ref_run_chain.restype = C.c_longlong
+        L.ref_run_chain.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_ulonglong,
+                                    C.c_uint, C.c_float, C.c_int, C.c_void_p, C.c_ulonglong,
+                                    C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def run_chain(self, stages, data, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
+        src = _as_u8(data)
+        if nbits is None:
+            nbits = src.size * 8
+        if out_cap is None:
+            out_cap = max(4096, src.size * 24 + 4096)
+        names = [STAGE_TO_CLI[s][0].encode() for s in stages]
+        enc = [STAGE_TO_CLI[s][1] for s in stages]
+        c_names = (C.c_char_p * len(stages))(*names)
+        c_enc = (C.c_int * len(stages))(*enc)
+        out = np.zeros(out_cap, dtype=np.uint8)
+        out_bits = C.c_ulonglong(0)
+        failed = C.c_int(-1)
+        rc = self.lib.ref_run_chain(c_names, c_enc, len(stages), src.ctypes.data if src.size else None, nbits, vs, nf,
+                                    int(adaptive), out.ctypes.data, out_cap, C.byref(out_bits), C.byref(failed))
+        nb = int(out_bits.value)
+        return int(rc), out[: (nb + 7) // 8].tobytes(), nb
+
+    def dega_encode(self, samples, vs=32, nf=100.0, adaptive=1):
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        return self.run_chain(DEGA_ENC, x, x.size * 32, vs, nf, adaptive)
+
+    def dega_decode(self, payload, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
+        rc, raw, nb = self.run_chain(DEGA_DEC, payload, nbits, vs, nf, adaptive, out_cap=out_cap)
+        return rc, np.frombuffer(raw[: (nb // 32) * 4], dtype=np.float32).copy()

@@ -1,0 +1,157 @@
+/* ref_driver.c -- in-process driver for the UNMODIFIED reference codecs (test infrastructure only).
+ *
+ * Linked by oracle/Makefile against objects compiled directly from
+ * /root/reference/DataCompressor/{DCIOLib,DCLib}/src/*.c (release flags of
+ * common/build/gcc/common.mak:11-20) into oracle/_ref/libdcref.so.  It replays what DCCLI's stage
+ * loop does (DCCLI/src/cli.c:430-466): every stage runs to completion on in-memory bit buffers and
+ * the write->read mode switch keeps the fractional last byte (cli.c:212-223), so stage N+1 sees the
+ * exact bit count stage N wrote.  None of this file is copied from the reference; it only calls its
+ * public API (DCLib/inc/enc_dec.h, DCIOLib/inc/bit_file_buffer.h, DCIOLib/inc/file_buffer.h).
+ *
+ * The reference codecs keep state in statics (bac.c:33-37,83-84; lzmh.c:139,143,396): one call at a
+ * time per process.  Parallel CPU baselines fork one process per worker.
+ */
+#include "err_codes.h"
+#include "enc_dec.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define REF_MAX_STAGES 16
+
+typedef struct mem_bits
+{
+  file_buffer_t *fb;
+  bit_file_buffer_t *bb;
+} mem_bits;
+
+static int mem_bits_open(mem_bits *m, file_buffer_mode_t mode)
+{
+  m->fb = AllocateFileBuffer();
+  m->bb = AllocateBitFileBuffer();
+  if (m->fb == NULL || m->bb == NULL)
+    return ERROR_MEMORY;
+  if (InitFileBufferInMemory(m->fb, mode, 2048) != NO_ERROR)
+    return ERROR_LIBRARY_INIT;
+  InitBitFileBuffer(m->bb, m->fb);
+  return NO_ERROR;
+}
+
+static void mem_bits_close(mem_bits *m)
+{
+  if (m->fb != NULL)
+  {
+    UninitFileBuffer(m->fb);
+    FreeFileBuffer(m->fb);
+  }
+  if (m->bb != NULL)
+    FreeBitFileBuffer(m->bb);
+  m->fb = NULL;
+  m->bb = NULL;
+}
+
+/* Runs `nstages` reference stages back to back.
+   names[i]   : encoder name as given on the DCCLI command line ("normalize", "diff", "seg", "bac", "lzmh", ...)
+   encode[i]  : 1 = "encode <name>", 0 = "decode <name>"
+   vs, nf, adaptive are applied to every stage (DCCLI takes them per stage; the tests always repeat them).
+   Input: `in_bits` bits, MSB-first, in `in`.  Output: exact bit count in *out_bits, bytes zero padded.
+   Returns the failing stage's (negative) code, or 0.  *failed_stage = index of the failing stage or -1. */
+long long ref_run_chain(const char *const *names, const int *encode, int nstages,
+                        const unsigned char *in, unsigned long long in_bits,
+                        unsigned vs, float nf, int adaptive,
+                        unsigned char *out, unsigned long long out_cap, unsigned long long *out_bits,
+                        int *failed_stage)
+{
+  mem_bits a, b;
+  mem_bits *rd = &a, *wr = &b;
+  io_int_t ret = NO_ERROR;
+  int i;
+  *out_bits = 0;
+  *failed_stage = -1;
+  a.fb = b.fb = NULL;
+  a.bb = b.bb = NULL;
+  if (nstages < 1 || nstages > REF_MAX_STAGES)
+    return ERROR_INVALID_VALUE;
+  if (mem_bits_open(rd, FBM_WRITING) != NO_ERROR || mem_bits_open(wr, FBM_WRITING) != NO_ERROR)
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_INIT;
+  }
+  /* Load the input with its exact bit count, then flip to reading (what SwitchTempBuffers does). */
+  if (in_bits > 0 && WriteBitFileBuffer(rd->bb, in, (size_t)in_bits) != (io_int_t)in_bits)
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_CALL;
+  }
+  SetBitFileBufferMode(rd->bb, FBM_READING);
+  for (i = 0; i < nstages; i++)
+  {
+    options_t opt;
+    const enc_dec_t *ed = GetEncoder(names[i]);
+    enc_dec_function_t *fn;
+    mem_bits *tmp;
+    if (ed == NULL)
+    {
+      ret = ERROR_INVALID_VALUE;
+      *failed_stage = i;
+      break;
+    }
+    memset(&opt, 0, sizeof(opt));
+    SetDefaultOptions(&opt);
+    opt.error_log_file = NULL;              /* LOG tolerates NULL, common/inc/log.h:10-13 */
+    opt.encode = encode[i];
+    opt.encoder_decoder = ed;
+    opt.value_size_bits = vs;
+    opt.normalization_factor = nf;
+    opt.adaptive = adaptive;
+    fn = encode[i] ? ed->encoder : ed->decoder;
+    if (fn == NULL)
+    {
+      ret = ERROR_INVALID_MODE;
+      *failed_stage = i;
+      break;
+    }
+    ret = (*fn)(rd->bb, wr->bb, &opt);
+    /* the written buffer becomes the next stage's input, also after an error (partial output) */
+    SetBitFileBufferMode(wr->bb, FBM_READING);
+    tmp = rd;
+    rd = wr;
+    wr = tmp;
+    if (ret != NO_ERROR)
+    {
+      *failed_stage = i;
+      break;
+    }
+    if (i + 1 < nstages)
+      ResetBitFileBuffer(wr->bb, FBM_WRITING);
+  }
+  /* Drain the final buffer: bytes first, then the fractional byte. */
+  {
+    unsigned long long total = 0;
+    io_int_t got;
+    for (;;)
+    {
+      unsigned char chunk[4096];
+      if (EndOfBitFileBuffer(rd->bb))
+        break;
+      got = ReadBitFileBuffer(rd->bb, chunk, sizeof(chunk) * 8);
+      if (got <= 0)
+        break;
+      if ((total + (unsigned long long)got + 7) / 8 > out_cap)
+      {
+        ret = ERROR_MEMORY;
+        break;
+      }
+      memcpy(out + total / 8, chunk, (size_t)((got + 7) / 8));   /* total is a multiple of 8 until the last chunk */
+      total += (unsigned long long)got;
+      if ((size_t)got != sizeof(chunk) * 8)
+        break;
+    }
+    *out_bits = total;
+  }
+  mem_bits_close(&a);
+  mem_bits_close(&b);
+  return ret;
+}
