@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- DEGA encode+decode throughput on B200 (BASELINE.json metric) with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path on the host cores
+
+Workload = BASELINE.json configs[1]: synthetic REDD-like 1 Hz load profiles, 4096 channels x 1 day per GPU,
+DEGA (normalize -> diff -> seg -> bac adaptive) encode + decode, channels cut into resumable 1024-sample blocks.
+A "step" is one encode + one decode of every stream on the rank.  `value` counts the raw float32 bytes once per
+step (GB/s of raw samples through the encode+decode round trip), inputs resident in HBM; `e2e` is the same
+step through the host-buffer C ABI (dc_dega_encode_host / dc_dega_decode_host) with pinned host memory.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CHANNELS = 4096
+SAMPLES = 86400
+BLOCK_LEN = 1024
+VS, NF, ADAPTIVE = 32, 100.0, True
+METRIC = "DEGA encode+decode GB/s of raw samples"
+
+
+def workload_name(channels, samples, block_len):
+    return (f"configs[1]: synthetic REDD-like 1 Hz load profiles, {channels} channels x {samples} samples per GPU, DEGA "
+            f"(normalize->diff->seg->bac adaptive) encode+decode, block_len {block_len}, valuesize {VS}, normalization_factor {NF:g}")
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own code (oracle/_ref, unmodified sources) on all host cores, one worker process
+# per core because the reference codecs are not re-entrant; falls back to the oracle port if _ref did not travel.
+def _cpu_worker(args):
+    kind, blocks, vs, nf, adaptive = args
+    import numpy as np
+    from oracle import binding
+    impl = binding.Ref() if kind == "reference" else binding.Oracle()
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for xs in blocks:
+        rc, pay, nb = impl.dega_encode(xs, vs, nf, adaptive)
+        assert rc == 0
+        rc, y = impl.dega_decode(pay, nb, vs, nf, adaptive, out_cap=xs.size * 4 + 64)
+        assert rc == 0 and np.array_equal(y.view(np.uint32), xs.view(np.uint32))
+        out_bytes += (nb + 7) // 8
+    return time.perf_counter() - t0, out_bytes
+
+
+def cpu_baseline_run(sample_blocks, cores, kind):
+    """sample_blocks: list of float32 arrays (streams).  Returns (GB/s of raw samples for encode+decode, seconds)."""
+    import multiprocessing as mp
+    shards = [sample_blocks[i::cores] for i in range(cores)]
+    shards = [s for s in shards if s]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(shards)) as pool:
+        res = pool.map(_cpu_worker, [(kind, s, VS, NF, int(ADAPTIVE)) for s in shards])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)          # excludes interpreter start-up of the workers
+    raw = sum(b.size for b in sample_blocks) * 4
+    return raw / busy / 1e9, busy, wall
+
+
+def cpu_kind():
+    from oracle import binding
+    return "reference" if binding.Ref.available() else "port"
+
+
+def cpu_sample(n_blocks, block_len, seed=0xDC0000):
+    """Host copy of the first n_blocks streams of the bench workload (same generator, same seed)."""
+    from data_compressor_b200 import synth
+    per_channel = (SAMPLES + block_len - 1) // block_len
+    n_ch = (n_blocks + per_channel - 1) // per_channel
+    x = synth.redd_like(n_ch, SAMPLES, device="cpu", seed=seed).numpy()
+    blocks = []
+    for c in range(n_ch):
+        for b in range(per_channel):
+            if len(blocks) < n_blocks:
+                blocks.append(x[c, b * block_len:(b + 1) * block_len].copy())
+    return blocks
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding
+    binding.build(ref=os.path.isdir("/root/reference/DataCompressor"))
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    # ~2 MB/s per core for encode, ~1.7 MB/s for decode: size one step to a few seconds per core
+    blocks_per_core = max(1, int(args.cpu_seconds * 0.9e6 / (args.block_len * 4)))
+    blocks = cpu_sample(blocks_per_core * cores, args.block_len)
+    for _ in range(args.warmup):
+        cpu_baseline_run(blocks[: cores * 4], cores, kind)
+    gbs, secs = [], []
+    for _ in range(args.steps):
+        g, busy, wall = cpu_baseline_run(blocks, cores, kind)
+        gbs.append(g)
+        secs.append(busy)
+    v = sum(b.size for b in blocks) * 4 * len(gbs) / sum(secs) / 1e9
+    sample = f"{len(blocks)} streams of {args.block_len} samples ({sum(b.size for b in blocks) * 4 / 1e6:.1f} MB raw) per step, same generator"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32/i64", "data": "synthetic",
+        "config": {"workload": workload_name(args.channels, args.samples, args.block_len), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from data_compressor_b200 import Context, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: data_compressor_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = Context(local)
+    C_, S_, L_ = args.channels, args.samples, args.block_len
+    # shard = this rank's channels (weak scaling: every GPU gets its own 4096 channels, disjoint seeds)
+    x = synth.redd_like(C_, S_, device=dev, seed=0xDC0000 + rank * C_)
+    raw_bytes = x.numel() * 4
+    n_streams = ctx.n_streams(C_, S_, L_)
+
+    enc = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)       # allocates outputs + arena once
+    y = torch.empty_like(x)
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
+        if world > 1:   # the only collective on the path: per-shard payload byte counts -> container offsets
+            mine = torch.tensor([e.total_bytes], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(sizes, mine)
+        ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+        return e
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms = {}
+    t_enc = t_dec = 0.0
+    with torch.cuda.stream(ctx.stream):
+        ev0.record(ctx.stream)
+        for _ in range(args.steps):
+            e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
+            km = ctx.kernel_ms()
+            if world > 1:
+                mine = torch.tensor([e.total_bytes], dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(sizes, mine)
+            ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+            km2 = ctx.kernel_ms()
+            for k, v in list(km.items()) + list(km2.items()):
+                kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+        ev1.record(ctx.stream)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    sampler.stop()
+    ctx.set_profiling(False)
+    ok = bool(torch.equal(y.view(torch.int32), x.view(torch.int32))) and not bool(enc.status.any().item())
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    tot_bytes = torch.tensor([float(enc.total_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_bytes, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * raw_bytes / (ms_per_step * 1e-3) / 1e9
+    kernel_ms = {k: v / args.steps for k, v in kernel_ms.items()}
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((C_, S_), dtype=torch.float32, pin_memory=True)
+        hx.copy_(x)
+        torch.cuda.synchronize(dev)
+        hxn = hx.numpy()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)     # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
+            yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all())
+        meta = n_streams * (8 + 8 + 4) + 8
+        e2e = {"value": world * raw_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(raw_bytes + pay.size + meta), "d2h_bytes_per_step": int(raw_bytes + pay.size + 2 * meta),
+               "api": "dc_dega_encode_host + dc_dega_decode_host (include/dc_cuda.h), host buffers, copies inside the timed region"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (4*N read + ceil(bits/8) written per stream)
+    peak, peak_src = measured_peak()
+    alg_bytes = raw_bytes + enc.total_bytes
+    dom = max(("bac_encode", "bac_decode"), key=lambda k: kernel_ms.get(k, 0.0))
+    dom_ms = kernel_ms.get(dom, 0.0)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dom_ms,
+                "note": "the coder is sequential per stream and integer-issue bound, see DESIGN.md section 4"}
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            kind = cpu_kind()
+            cores = os.cpu_count() or 1
+            blocks_per_core = max(1, int(args.cpu_seconds * 0.9e6 / (L_ * 4)))
+            blocks = cpu_sample(blocks_per_core * cores, L_)
+            g, busy, wall = cpu_baseline_run(blocks, cores, kind)
+            cpu = {"value": g, "unit": "GB/s", "cores": cores, "kind": kind, "seconds": busy,
+                   "sample": f"{len(blocks)} streams of {L_} samples ({sum(b.size for b in blocks) * 4 / 1e6:.1f} MB raw), encode+decode, "
+                             f"one worker process per core, in-process calls (no DCCLI spawn / file I/O)"}
+        except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line
+            cpu = {"value": None, "error": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/i64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(C_, S_, L_), "streams_per_gpu": n_streams, "raw_bytes_per_gpu": raw_bytes,
+                   "l2": "inputs (1.4 GB per GPU) are larger than the 126 MB L2; no flush needed", "parallelism": f"channels sharded over {world} GPU(s)"},
+        "compression_ratio": world * raw_bytes / float(tot_bytes.item()),
+        "encode_ms": sum(kernel_ms.get(k, 0.0) for k in ("front", "bac_encode", "scan", "gather")),
+        "decode_ms": sum(kernel_ms.get(k, 0.0) for k in ("bac_decode", "back")),
+        "kernel_ms": kernel_ms, "round_trip_ok": ok,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=CHANNELS)
+    ap.add_argument("--samples", type=int, default=SAMPLES)
+    ap.add_argument("--block-len", type=int, default=BLOCK_LEN)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU-baseline work per core")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

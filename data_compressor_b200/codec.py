@@ -1,0 +1,228 @@
+"""Batch face of the hot path: many independent streams per call, device-resident (torch tensors).
+
+torch is plumbing here (device memory, streams, events); every codec result comes from the hand-written sm_100a
+kernels behind include/dc_cuda.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DcError, Layout, Params
+
+
+@dataclass
+class Encoded:
+    """Container-ready result of a batch encode (all tensors on the GPU).
+
+    payload[byte_off[s] : byte_off[s] + ceil(bit_len[s] / 8)] is byte-identical to the file DCCLI writes for
+    stream s (DCIOLib/src/bit_file_buffer.c:310-333)."""
+    payload: torch.Tensor      # uint8 [capacity]; first total_bytes are valid
+    bit_len: torch.Tensor      # int64 [n_streams]
+    byte_off: torch.Tensor     # int64 [n_streams + 1]
+    status: torch.Tensor       # int32 [n_streams]
+    total_bytes: int
+    n_channels: int
+    channel_len: int
+    block_len: int
+
+    @property
+    def n_streams(self) -> int:
+        return int(self.bit_len.numel())
+
+    def stream_bytes(self, s: int) -> bytes:
+        o = int(self.byte_off[s])
+        n = (int(self.bit_len[s]) + 7) // 8
+        return bytes(self.payload[o:o + n].cpu().numpy().tobytes())
+
+
+class Context:
+    """One dc_ctx: one GPU, one CUDA stream, one scratch arena.  Not re-entrant (like the reference codecs)."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise DcError(_lib.ERR_LIBRARY_INIT, "no CUDA device: data_compressor_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.dc_create(C.byref(h), self.device)
+        if rc != 0:
+            raise DcError(rc, "dc_create")
+        self.h = h
+        self.torch_device = torch.device("cuda", self.device)
+        self.stream = torch.cuda.ExternalStream(self.lib.dc_stream(self.h), device=self.torch_device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise DcError(rc, f"{what}: {self.lib.dc_last_error(self.h).decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.dc_launch_count(self.h))
+
+    def set_profiling(self, enable: bool):
+        self._check(self.lib.dc_set_profiling(self.h, 1 if enable else 0), "dc_set_profiling")
+
+    def kernel_ms(self) -> dict:
+        """Device time (ms) of each kernel group during the last call (CUDA events on the context's stream)."""
+        arr = (C.c_float * len(_lib.KERNEL_NAMES))()
+        self._check(self.lib.dc_get_kernel_ms(self.h, arr), "dc_get_kernel_ms")
+        return {k: float(arr[i]) for i, k in enumerate(_lib.KERNEL_NAMES)}
+
+    def synchronize(self):
+        self._check(self.lib.dc_synchronize(self.h), "dc_synchronize")
+
+    @staticmethod
+    def _params(vs: int, nf: float, adaptive: bool) -> Params:
+        return Params(int(vs), float(nf), 1 if adaptive else 0, 0)
+
+    @staticmethod
+    def _layout(n_channels: int, channel_len: int, block_len: int) -> Layout:
+        return Layout(int(n_channels), int(channel_len), int(block_len), 0, None)
+
+    def n_streams(self, n_channels: int, channel_len: int, block_len: int) -> int:
+        lay = self._layout(n_channels, channel_len, block_len)
+        return int(self.lib.dc_layout_streams(C.byref(lay)))
+
+    # ------------------------------------------------------------------------------------------------
+    def _encode(self, fn, what, samples, block_len, vs, nf, adaptive, payload, payload_cap, out):
+        assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous() and samples.dim() == 2
+        n_channels, channel_len = samples.shape
+        n = self.n_streams(n_channels, channel_len, block_len)
+        dev = samples.device
+        if out is None:
+            if payload_cap is None:
+                # generous default: raw size + per-stream slack (DEGA never expands REDD-like data)
+                payload_cap = samples.numel() * 4 + n * 16 + 64
+            payload = torch.empty(int(payload_cap) + 16, dtype=torch.uint8, device=dev)
+            bit_len = torch.empty(n, dtype=torch.int64, device=dev)
+            byte_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            status = torch.empty(n, dtype=torch.int32, device=dev)
+        else:
+            payload, bit_len, byte_off, status = out.payload, out.bit_len, out.byte_off, out.status
+            payload_cap = payload.numel() - 16
+        lay = self._layout(n_channels, channel_len, block_len)
+        par = self._params(vs, nf, adaptive)
+        total = C.c_uint64(0)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = fn(self.h, samples.data_ptr(), C.byref(lay), C.byref(par), payload.data_ptr(), int(payload_cap),
+                bit_len.data_ptr(), byte_off.data_ptr(), status.data_ptr(), C.byref(total))
+        self._check(rc, what)
+        return Encoded(payload, bit_len, byte_off, status, int(total.value), n_channels, channel_len, int(block_len))
+
+    def dega_encode(self, samples: torch.Tensor, block_len: int = 0, vs: int = 32, nf: float = 100.0,
+                    adaptive: bool = True, payload_cap: int | None = None, out: Encoded | None = None) -> Encoded:
+        """`encode normalize # encode diff # encode seg # encode bac [adaptive]` for every (channel, block).
+
+        samples: float32 [n_channels, channel_len] on the GPU (one raw float32 "file" per channel);
+        block_len: samples per resumable block, 0 = whole channel."""
+        return self._encode(self.lib.dc_dega_encode_device, "dc_dega_encode_device", samples, block_len, vs, nf,
+                            adaptive, None, payload_cap, out)
+
+    def axdr_encode(self, samples: torch.Tensor, block_len: int = 0, vs: int = 32, nf: float = 100.0,
+                    payload_cap: int | None = None, out: Encoded | None = None) -> Encoded:
+        """`encode normalize` (A-XDR) for every stream."""
+        return self._encode(self.lib.dc_axdr_encode_device, "dc_axdr_encode_device", samples, block_len, vs, nf,
+                            False, None, payload_cap, out)
+
+    def _decode(self, fn, what, enc: Encoded, vs, nf, adaptive, out):
+        dev = enc.payload.device
+        n = enc.n_streams
+        if out is None:
+            out = torch.empty((enc.n_channels, enc.channel_len), dtype=torch.float32, device=dev)
+        n_out = torch.empty(n, dtype=torch.int64, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        lay = self._layout(enc.n_channels, enc.channel_len, enc.block_len)
+        par = self._params(vs, nf, adaptive)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = fn(self.h, enc.payload.data_ptr(), int(enc.total_bytes), enc.bit_len.data_ptr(), enc.byte_off.data_ptr(),
+                C.byref(lay), C.byref(par), out.data_ptr(), n_out.data_ptr(), status.data_ptr())
+        self._check(rc, what)
+        self.synchronize()
+        return out, n_out, status
+
+    def dega_decode(self, enc: Encoded, vs: int = 32, nf: float = 100.0, adaptive: bool = True,
+                    out: torch.Tensor | None = None):
+        """`decode bac [adaptive] # decode seg # decode diff # decode normalize` for every stream.
+
+        Returns (samples [n_channels, channel_len], n_out [n_streams], status [n_streams])."""
+        return self._decode(self.lib.dc_dega_decode_device, "dc_dega_decode_device", enc, vs, nf, adaptive, out)
+
+    def axdr_decode(self, enc: Encoded, vs: int = 32, nf: float = 100.0, out: torch.Tensor | None = None):
+        return self._decode(self.lib.dc_axdr_decode_device, "dc_axdr_decode_device", enc, vs, nf, False, out)
+
+    # ---- host-buffer face (numpy in / numpy out; copies inside) -----------------------------------
+    def dega_encode_host(self, samples: np.ndarray, block_len: int = 0, vs: int = 32, nf: float = 100.0,
+                         adaptive: bool = True, payload_cap: int | None = None):
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        assert x.ndim == 2
+        n_channels, channel_len = x.shape
+        n = self.n_streams(n_channels, channel_len, block_len)
+        if payload_cap is None:
+            payload_cap = x.size * 4 + n * 16 + 64
+        payload = np.empty(payload_cap, dtype=np.uint8)
+        bit_len = np.empty(n, dtype=np.uint64)
+        byte_off = np.empty(n + 1, dtype=np.uint64)
+        status = np.empty(n, dtype=np.int32)
+        total = C.c_uint64(0)
+        lay = self._layout(n_channels, channel_len, block_len)
+        par = self._params(vs, nf, adaptive)
+        rc = self.lib.dc_dega_encode_host(self.h, x.ctypes.data, C.byref(lay), C.byref(par), payload.ctypes.data,
+                                          payload_cap, bit_len.ctypes.data, byte_off.ctypes.data, status.ctypes.data,
+                                          C.byref(total))
+        self._check(rc, "dc_dega_encode_host")
+        return payload[: total.value], bit_len, byte_off, status
+
+    def dega_decode_host(self, payload: np.ndarray, bit_len: np.ndarray, byte_off: np.ndarray, n_channels: int,
+                         channel_len: int, block_len: int = 0, vs: int = 32, nf: float = 100.0, adaptive: bool = True):
+        p = np.ascontiguousarray(payload, dtype=np.uint8)
+        bl = np.ascontiguousarray(bit_len, dtype=np.uint64)
+        bo = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        n = bl.size
+        out = np.empty((n_channels, channel_len), dtype=np.float32)
+        n_out = np.empty(n, dtype=np.uint64)
+        status = np.empty(n, dtype=np.int32)
+        lay = self._layout(n_channels, channel_len, block_len)
+        par = self._params(vs, nf, adaptive)
+        rc = self.lib.dc_dega_decode_host(self.h, p.ctypes.data, p.size, bl.ctypes.data, bo.ctypes.data, C.byref(lay),
+                                          C.byref(par), out.ctypes.data, n_out.ctypes.data, status.ctypes.data)
+        self._check(rc, "dc_dega_decode_host")
+        return out, n_out, status
+
+    # ---- plugin face: one stage, one stream, host bytes -------------------------------------------
+    def stage_run(self, stage: int, data, nbits: int | None = None, vs: int = 32, nf: float = 100.0,
+                  adaptive: bool = False):
+        """Runs ONE reference stage on the GPU (what an enc_dec_function_t body calls).  Returns
+        (code, bytes, nbits): code is 0 or the negative err_codes.h value the reference stage returns."""
+        src = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        if nbits is None:
+            nbits = src.size * 8
+        par = self._params(vs, nf, adaptive)
+        cap = int(self.lib.dc_stage_out_bound(stage, nbits, C.byref(par)))
+        out_bits = C.c_uint64(0)
+        for _ in range(3):
+            out = np.empty(max(cap, 16), dtype=np.uint8)
+            rc = self.lib.dc_stage_run_host(self.h, stage, src.ctypes.data if src.size else None, nbits, C.byref(par),
+                                            out.ctypes.data, out.size, C.byref(out_bits))
+            if rc == _lib.ERR_MEMORY and out_bits.value and (out_bits.value + 7) // 8 > out.size:
+                cap = (out_bits.value + 7) // 8 + 16     # exact size reported: retry once
+                continue
+            break
+        nb = int(out_bits.value) if rc == 0 else 0
+        return rc, out[: (nb + 7) // 8].tobytes(), nb

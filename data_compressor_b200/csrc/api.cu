@@ -1,0 +1,931 @@
+// api.cu -- host side of the C ABI declared in include/dc_cuda.h.
+//
+// No CPU fallback anywhere in this file: every codec result is produced by the kernels in dega_kernels.cu /
+// lzmh_kernels.cu.  Without a usable GPU dc_create() fails with DC_ERR_LIBRARY_INIT.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/dc_cuda.h"
+#include "kernels.h"
+
+using namespace dc;
+
+struct dc_ctx
+{
+  int device;
+  cudaStream_t stream;
+  DivEntry *d_div;
+  uint8_t *arena;
+  uint64_t arena_size;
+  uint64_t arena_used;
+  uint64_t *h_pinned;   // small pinned mailbox for device->host scalars
+  uint64_t launches_base;
+  int profiling;
+  cudaEvent_t ev[2 * DC_K_COUNT];
+  uint32_t ev_mask;   // kernels timed during the last call
+  char err[256];
+};
+
+namespace {
+
+void set_err(dc_ctx *c, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(c->err, sizeof(c->err), fmt, ap);
+  va_end(ap);
+}
+
+#define CU_TRY(ctx, call, code)                                                                          \
+  do                                                                                                      \
+  {                                                                                                       \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+    {                                                                                                     \
+      set_err((ctx), "%s failed: %s", #call, cudaGetErrorString(e__));                                    \
+      return (code);                                                                                      \
+    }                                                                                                     \
+  } while (0)
+
+uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// RAII: CUDA events around one kernel group when profiling is on
+struct Timed
+{
+  dc_ctx *c;
+  int id;
+  Timed(dc_ctx *ctx, int kernel_id) : c(ctx), id(kernel_id)
+  {
+    if (c->profiling)
+      cudaEventRecord(c->ev[2 * id], c->stream);
+  }
+  ~Timed()
+  {
+    if (c->profiling)
+    {
+      cudaEventRecord(c->ev[2 * id + 1], c->stream);
+      c->ev_mask |= 1u << id;
+    }
+  }
+};
+
+// Bump allocator over one device block; grown (with a synchronise) when a call needs more.
+int arena_reserve(dc_ctx *c, uint64_t bytes)
+{
+  if (bytes <= c->arena_size)
+    return DC_OK;
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  if (c->arena)
+    cudaFree(c->arena);
+  c->arena = nullptr;
+  c->arena_size = 0;
+  const uint64_t want = round_up(bytes + bytes / 8, 1 << 20);
+  if (cudaMalloc(&c->arena, want) != cudaSuccess)
+  {
+    cudaGetLastError();
+    if (cudaMalloc(&c->arena, round_up(bytes, 1 << 20)) != cudaSuccess)
+    {
+      cudaGetLastError();
+      set_err(c, "device scratch allocation of %llu bytes failed", (unsigned long long)bytes);
+      return DC_ERR_MEMORY;
+    }
+    c->arena_size = round_up(bytes, 1 << 20);
+    return DC_OK;
+  }
+  c->arena_size = want;
+  return DC_OK;
+}
+
+struct Bump
+{
+  uint8_t *base;
+  uint64_t used;
+  explicit Bump(uint8_t *b) : base(b), used(0) {}
+  template <typename T>
+  T *take(uint64_t count)
+  {
+    T *p = reinterpret_cast<T *>(base + used);
+    used += round_up(count * sizeof(T), 256);
+    return p;
+  }
+  static uint64_t size_of(uint64_t count, uint64_t elem) { return round_up(count * elem, 256); }
+};
+
+bool params_ok(const dc_params *p) { return p && p->value_size_bits >= 1 && p->value_size_bits <= 64; }
+
+// dc_layout -> device Layout; max_len = longest stream (needs sample_off on the host for ragged mode)
+int make_layout(dc_ctx *c, const dc_layout *in, const uint64_t *host_off, Layout &L, uint64_t &max_len, uint64_t &total_samples)
+{
+  if (!in)
+    return DC_ERR_INVALID_VALUE;
+  if (in->sample_off == nullptr)
+  {
+    const uint64_t bl = in->block_len == 0 ? std::max<uint64_t>(in->channel_len, 1) : in->block_len;
+    const uint64_t bpc = in->channel_len == 0 ? 1 : (in->channel_len + bl - 1) / bl;
+    L.n_streams = in->n_channels * bpc;
+    L.channel_len = in->channel_len;
+    L.block_len = bl;
+    L.blocks_per_channel = bpc;
+    L.sample_off = nullptr;
+    max_len = std::min(bl, in->channel_len);
+    total_samples = in->n_channels * in->channel_len;
+    return DC_OK;
+  }
+  L.n_streams = in->n_streams;
+  L.channel_len = 0;
+  L.block_len = 0;
+  L.blocks_per_channel = 1;
+  L.sample_off = in->sample_off;
+  max_len = 0;
+  total_samples = 0;
+  if (host_off)
+  {
+    for (uint64_t s = 0; s < in->n_streams; s++)
+    {
+      if (host_off[s + 1] < host_off[s])
+      {
+        set_err(c, "sample_off is not monotonic at stream %llu", (unsigned long long)s);
+        return DC_ERR_INVALID_VALUE;
+      }
+      max_len = std::max(max_len, host_off[s + 1] - host_off[s]);
+    }
+    total_samples = in->n_streams ? host_off[in->n_streams] : 0;
+  }
+  return DC_OK;
+}
+
+// ragged device layouts: fetch the offsets once to size the scratch (not the performance path)
+int fetch_offsets(dc_ctx *c, const dc_layout *in, std::vector<uint64_t> &host_off)
+{
+  host_off.resize(in->n_streams + 1);
+  CU_TRY(c, cudaMemcpyAsync(host_off.data(), in->sample_off, (in->n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream),
+         DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  return DC_OK;
+}
+
+uint64_t seg_cap_bytes(uint64_t max_len, uint32_t vs) { return round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16); }
+uint64_t fixed_cap_bytes(uint64_t max_len, uint32_t vs) { return round_up((max_len * (uint64_t)vs + 7) / 8 + 8, 16); }
+uint64_t bac_cap_bytes(uint64_t in_cap_bytes, int adaptive, unsigned boost)
+{
+  // adaptive frequency counting costs at most ~1 bit per input bit plus O(log n); the static 1/3-1/3-1/3
+  // model costs log2(3) bits per input bit.  `boost` multiplies the estimate after a reported overflow.
+  const uint64_t est = adaptive ? in_cap_bytes + in_cap_bytes / 8 : in_cap_bytes * 13 / 8;
+  return round_up(est * boost + 64, 16);
+}
+
+int check_launch(dc_ctx *c, const char *what)
+{
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_err(c, "%s: %s", what, cudaGetErrorString(e));
+    return DC_ERR_LIBRARY_CALL;
+  }
+  return DC_OK;
+}
+
+// Reads `count` uint64 from the device through the pinned mailbox (synchronises the stream).
+int read_back(dc_ctx *c, const uint64_t *d_src, uint64_t *dst, int count)
+{
+  CU_TRY(c, cudaMemcpyAsync(c->h_pinned, d_src, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_err(c, "kernel execution failed: %s", cudaGetErrorString(e));
+    return DC_ERR_LIBRARY_CALL;
+  }
+  for (int i = 0; i < count; i++)
+    dst[i] = c->h_pinned[i];
+  return DC_OK;
+}
+
+// ---- encode pipeline: front end -> [bac] -> scan -> gather ----------------------------------------------
+enum FrontKind { FRONT_DEGA, FRONT_AXDR };
+
+int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Layout &L, uint64_t max_len, const dc_params *p,
+                    uint8_t *d_payload, uint64_t payload_cap, uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status,
+                    uint64_t *total_bytes)
+{
+  const uint64_t n = L.n_streams;
+  const uint32_t vs = p->value_size_bits;
+  c->ev_mask = 0;
+  for (unsigned boost = 1;; boost *= 8)
+  {
+    const uint64_t front_cap = kind == FRONT_DEGA ? seg_cap_bytes(max_len, vs) : fixed_cap_bytes(max_len, vs);
+    const uint64_t bac_cap = kind == FRONT_DEGA ? bac_cap_bytes(front_cap, p->adaptive, boost) : 0;
+    const uint64_t n_tiles = (n + 4095) / 4096;
+    const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(n_tiles + 2, 8) + Bump::size_of(2, 8) + Bump::size_of(n * front_cap, 1) +
+                          Bump::size_of(n * bac_cap, 1) + 4096;
+    int rc = arena_reserve(c, need);
+    if (rc != DC_OK)
+      return rc;
+    Bump b(c->arena);
+    uint64_t *d_front_bits = b.take<uint64_t>(n);
+    uint64_t *d_tiles = b.take<uint64_t>(n_tiles + 2);
+    uint64_t *d_flags = b.take<uint64_t>(2);
+    uint8_t *d_front = b.take<uint8_t>(n * front_cap);
+    uint8_t *d_bac = b.take<uint8_t>(n * bac_cap);
+
+    CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
+
+    FrontArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.lay = L;
+    fa.samples = d_samples;
+    fa.in_is_float = 1;
+    fa.do_norm = 1;
+    fa.do_diff = kind == FRONT_DEGA;
+    fa.out_seg = kind == FRONT_DEGA;
+    fa.vs = vs;
+    fa.nf = p->normalization_factor;
+    fa.out.base = d_front;
+    fa.out.stride_bytes = front_cap;
+    fa.out.nbits = kind == FRONT_DEGA ? d_front_bits : d_bit_len;
+    fa.status = d_status;
+    {
+      Timed t(c, DC_K_FRONT);
+      launch_front(fa, c->stream);
+    }
+    if ((rc = check_launch(c, "front_kernel")) != DC_OK)
+      return rc;
+
+    const uint8_t *d_final = d_front;
+    uint64_t final_stride = front_cap;
+    if (kind == FRONT_DEGA)
+    {
+      BacArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.n_streams = n;
+      ba.in.base = d_front;
+      ba.in.byte_off = nullptr;
+      ba.in.stride_bytes = front_cap;
+      ba.in.nbits = d_front_bits;
+      ba.out.base = d_bac;
+      ba.out.stride_bytes = bac_cap;
+      ba.out.nbits = d_bit_len;
+      ba.adaptive = p->adaptive;
+      ba.div_table = c->d_div;
+      ba.status = d_status;
+      ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_flags);
+      {
+        Timed t(c, DC_K_BAC_ENC);
+        launch_bac_encode(ba, c->stream);
+      }
+      if ((rc = check_launch(c, "bac_encode_kernel")) != DC_OK)
+        return rc;
+      d_final = d_bac;
+      final_stride = bac_cap;
+    }
+    {
+      Timed t(c, DC_K_SCAN);
+      launch_byte_scan(d_bit_len, n, d_byte_off, d_tiles, c->stream);
+    }
+    if ((rc = check_launch(c, "scan kernels")) != DC_OK)
+      return rc;
+    {
+      Timed t(c, DC_K_GATHER);
+      launch_gather(d_final, final_stride, d_bit_len, d_byte_off, n, d_payload, payload_cap, c->stream);
+    }
+    if ((rc = check_launch(c, "gather_kernel")) != DC_OK)
+      return rc;
+    // one synchronisation per call: total size + overflow flag
+    CU_TRY(c, cudaMemcpyAsync(d_flags + 1, d_byte_off + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    uint64_t host_flags[2];
+    if ((rc = read_back(c, d_flags, host_flags, 2)) != DC_OK)
+      return rc;
+    if (host_flags[0] != 0 && boost < 512)
+      continue;   // a stream outgrew the coder scratch: redo with a larger stride (never seen in practice)
+    if (host_flags[0] != 0)
+    {
+      set_err(c, "arithmetic coder output exceeded the scratch capacity");
+      return DC_ERR_MEMORY;
+    }
+    if (total_bytes)
+      *total_bytes = host_flags[1];
+    if (host_flags[1] > payload_cap)
+    {
+      set_err(c, "payload needs %llu bytes, capacity is %llu", (unsigned long long)host_flags[1], (unsigned long long)payload_cap);
+      return DC_ERR_MEMORY;
+    }
+    return DC_OK;
+  }
+}
+
+// ---- decode pipeline: [bac] -> back end ------------------------------------------------------------------
+int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const uint64_t *d_bit_len, const uint64_t *d_byte_off,
+                    const Layout &L, uint64_t max_len, const dc_params *p, float *d_samples, uint64_t *d_n_out, int32_t *d_status)
+{
+  const uint64_t n = L.n_streams;
+  const uint32_t vs = p->value_size_bits;
+  const uint64_t seg_cap = kind == FRONT_DEGA ? seg_cap_bytes(max_len, vs) : 0;
+  c->ev_mask = 0;
+  const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(2, 8) + Bump::size_of(n * seg_cap, 1) + 4096;
+  int rc = arena_reserve(c, need);
+  if (rc != DC_OK)
+    return rc;
+  Bump b(c->arena);
+  uint64_t *d_seg_bits = b.take<uint64_t>(n);
+  uint64_t *d_flags = b.take<uint64_t>(2);
+  uint8_t *d_seg = b.take<uint8_t>(n * seg_cap);
+
+  CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
+
+  BackArgs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.lay = L;
+  ka.n_streams = n;
+  ka.vs = vs;
+  ka.nf = p->normalization_factor;
+  ka.samples = d_samples;
+  ka.n_out = d_n_out;
+  ka.status = d_status;
+  ka.do_denorm = 1;
+  if (kind == FRONT_DEGA)
+  {
+    BacArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.n_streams = n;
+    ba.in.base = d_payload;
+    ba.in.byte_off = d_byte_off;
+    ba.in.nbits = d_bit_len;
+    ba.out.base = d_seg;
+    ba.out.stride_bytes = seg_cap;
+    ba.out.nbits = d_seg_bits;
+    ba.adaptive = p->adaptive;
+    ba.div_table = c->d_div;
+    ba.status = d_status;
+    ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_flags);
+    {
+      Timed t(c, DC_K_BAC_DEC);
+      launch_bac_decode(ba, c->stream);
+    }
+    if ((rc = check_launch(c, "bac_decode_kernel")) != DC_OK)
+      return rc;
+    ka.in.base = d_seg;
+    ka.in.byte_off = nullptr;
+    ka.in.stride_bytes = seg_cap;
+    ka.in.nbits = d_seg_bits;
+    ka.in_seg = 1;
+    ka.do_undiff = 1;
+  }
+  else
+  {
+    ka.in.base = d_payload;
+    ka.in.byte_off = d_byte_off;
+    ka.in.nbits = d_bit_len;
+    ka.in_seg = 0;
+    ka.do_undiff = 0;
+  }
+  {
+    Timed t(c, DC_K_BACK);
+    launch_back(ka, c->stream);
+  }
+  return check_launch(c, "back_kernel");
+}
+
+// Device staging buffers for the host-facing calls are plain cudaMalloc allocations owned by the call.
+struct DevBuf
+{
+  void *p = nullptr;
+  ~DevBuf()
+  {
+    if (p)
+      cudaFree(p);
+  }
+  int alloc(dc_ctx *c, uint64_t bytes)
+  {
+    if (cudaMalloc(&p, std::max<uint64_t>(bytes, 16)) != cudaSuccess)
+    {
+      cudaGetLastError();
+      set_err(c, "device allocation of %llu bytes failed", (unsigned long long)bytes);
+      p = nullptr;
+      return DC_ERR_MEMORY;
+    }
+    return DC_OK;
+  }
+  template <typename T>
+  T *as()
+  {
+    return static_cast<T *>(p);
+  }
+};
+
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dc_abi_version(void) { return DC_ABI_VERSION; }
+
+int dc_create(dc_ctx **out, int device)
+{
+  if (!out)
+    return DC_ERR_INVALID_VALUE;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+  {
+    cudaGetLastError();
+    return DC_ERR_LIBRARY_INIT;
+  }
+  dc_ctx *c = new (std::nothrow) dc_ctx;
+  if (!c)
+    return DC_ERR_MEMORY;
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    cudaGetLastError();
+    delete c;
+    return DC_ERR_LIBRARY_INIT;
+  }
+  std::vector<DivEntry> tab(kDivTableEntries);
+  build_div_table(tab.data());
+  if (cudaMalloc(&c->d_div, kDivTableEntries * sizeof(DivEntry)) != cudaSuccess ||
+      cudaMemcpy(c->d_div, tab.data(), kDivTableEntries * sizeof(DivEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMallocHost(&c->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess)
+  {
+    cudaGetLastError();
+    dc_destroy(c);
+    return DC_ERR_LIBRARY_INIT;
+  }
+  for (int i = 0; i < 2 * DC_K_COUNT; i++)
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess)
+    {
+      cudaGetLastError();
+      dc_destroy(c);
+      return DC_ERR_LIBRARY_INIT;
+    }
+  c->launches_base = launch_counter();
+  *out = c;
+  return DC_OK;
+}
+
+void dc_destroy(dc_ctx *c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  if (c->arena)
+    cudaFree(c->arena);
+  if (c->d_div)
+    cudaFree(c->d_div);
+  if (c->h_pinned)
+    cudaFreeHost(c->h_pinned);
+  for (int i = 0; i < 2 * DC_K_COUNT; i++)
+    if (c->ev[i])
+      cudaEventDestroy(c->ev[i]);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *dc_last_error(const dc_ctx *c) { return c ? c->err : "no context"; }
+
+uint64_t dc_layout_streams(const dc_layout *in)
+{
+  if (!in)
+    return 0;
+  if (in->sample_off)
+    return in->n_streams;
+  const uint64_t bl = in->block_len == 0 ? std::max<uint64_t>(in->channel_len, 1) : in->block_len;
+  const uint64_t bpc = in->channel_len == 0 ? 1 : (in->channel_len + bl - 1) / bl;
+  return in->n_channels * bpc;
+}
+
+int dc_synchronize(dc_ctx *c)
+{
+  if (!c)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  return DC_OK;
+}
+
+void *dc_stream(dc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+uint64_t dc_launch_count(const dc_ctx *c) { return c ? launch_counter() - c->launches_base : 0; }
+
+int dc_set_profiling(dc_ctx *c, int enable)
+{
+  if (!c)
+    return DC_ERR_INVALID_VALUE;
+  c->profiling = enable != 0;
+  c->ev_mask = 0;
+  return DC_OK;
+}
+
+int dc_get_kernel_ms(dc_ctx *c, float *ms)
+{
+  if (!c || !ms)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  for (int i = 0; i < DC_K_COUNT; i++)
+  {
+    ms[i] = 0.0f;
+    if (c->ev_mask & (1u << i))
+      CU_TRY(c, cudaEventElapsedTime(&ms[i], c->ev[2 * i], c->ev[2 * i + 1]), DC_ERR_LIBRARY_CALL);
+  }
+  return DC_OK;
+}
+
+// ---- DEGA / A-XDR, device buffers ---------------------------------------------------------------------------
+static int encode_device_common(dc_ctx *c, FrontKind kind, const float *d_samples, const dc_layout *layout, const dc_params *params,
+                                uint8_t *d_payload, uint64_t payload_cap, uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status,
+                                uint64_t *total_bytes)
+{
+  if (!c || !params_ok(params) || !layout || !d_bit_len || !d_byte_off || !d_status)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  std::vector<uint64_t> host_off;
+  if (layout->sample_off)
+  {
+    const int rc = fetch_offsets(c, layout, host_off);
+    if (rc != DC_OK)
+      return rc;
+  }
+  Layout L;
+  uint64_t max_len, total;
+  const int rc = make_layout(c, layout, layout->sample_off ? host_off.data() : nullptr, L, max_len, total);
+  if (rc != DC_OK)
+    return rc;
+  return encode_pipeline(c, kind, d_samples, L, max_len, params, d_payload, payload_cap, d_bit_len, d_byte_off, d_status, total_bytes);
+}
+
+static int decode_device_common(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, uint64_t payload_bytes, const uint64_t *d_bit_len,
+                                const uint64_t *d_byte_off, const dc_layout *layout, const dc_params *params, float *d_samples,
+                                uint64_t *d_n_out, int32_t *d_status)
+{
+  (void)payload_bytes;
+  if (!c || !params_ok(params) || !layout || !d_bit_len || !d_byte_off || !d_n_out || !d_status)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  std::vector<uint64_t> host_off;
+  if (layout->sample_off)
+  {
+    const int rc = fetch_offsets(c, layout, host_off);
+    if (rc != DC_OK)
+      return rc;
+  }
+  Layout L;
+  uint64_t max_len, total;
+  const int rc = make_layout(c, layout, layout->sample_off ? host_off.data() : nullptr, L, max_len, total);
+  if (rc != DC_OK)
+    return rc;
+  return decode_pipeline(c, kind, d_payload, d_bit_len, d_byte_off, L, max_len, params, d_samples, d_n_out, d_status);
+}
+
+int dc_dega_encode_device(dc_ctx *c, const float *d_samples, const dc_layout *layout, const dc_params *params, uint8_t *d_payload,
+                          uint64_t payload_cap, uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status, uint64_t *total_bytes)
+{
+  return encode_device_common(c, FRONT_DEGA, d_samples, layout, params, d_payload, payload_cap, d_bit_len, d_byte_off, d_status,
+                              total_bytes);
+}
+
+int dc_axdr_encode_device(dc_ctx *c, const float *d_samples, const dc_layout *layout, const dc_params *params, uint8_t *d_payload,
+                          uint64_t payload_cap, uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status, uint64_t *total_bytes)
+{
+  return encode_device_common(c, FRONT_AXDR, d_samples, layout, params, d_payload, payload_cap, d_bit_len, d_byte_off, d_status,
+                              total_bytes);
+}
+
+int dc_dega_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes, const uint64_t *d_bit_len,
+                          const uint64_t *d_byte_off, const dc_layout *layout, const dc_params *params, float *d_samples,
+                          uint64_t *d_n_out, int32_t *d_status)
+{
+  return decode_device_common(c, FRONT_DEGA, d_payload, payload_bytes, d_bit_len, d_byte_off, layout, params, d_samples, d_n_out,
+                              d_status);
+}
+
+int dc_axdr_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes, const uint64_t *d_bit_len,
+                          const uint64_t *d_byte_off, const dc_layout *layout, const dc_params *params, float *d_samples,
+                          uint64_t *d_n_out, int32_t *d_status)
+{
+  return decode_device_common(c, FRONT_AXDR, d_payload, payload_bytes, d_bit_len, d_byte_off, layout, params, d_samples, d_n_out,
+                              d_status);
+}
+
+// ---- DEGA, host buffers ----------------------------------------------------------------------------------
+int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout, const dc_params *params, uint8_t *payload,
+                        uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes)
+{
+  if (!c || !params_ok(params) || !layout)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  Layout L;
+  uint64_t max_len, total;
+  int rc = make_layout(c, layout, layout->sample_off, L, max_len, total);
+  if (rc != DC_OK)
+    return rc;
+  const uint64_t n = L.n_streams;
+  DevBuf d_samples, d_off, d_payload, d_bits, d_boff, d_status;
+  if ((rc = d_samples.alloc(c, total * 4)) || (rc = d_payload.alloc(c, round_up(payload_cap, 4) + 16)) || (rc = d_bits.alloc(c, n * 8)) ||
+      (rc = d_boff.alloc(c, (n + 1) * 8)) || (rc = d_status.alloc(c, n * 4)))
+    return rc;
+  if (layout->sample_off)
+  {
+    if ((rc = d_off.alloc(c, (n + 1) * 8)))
+      return rc;
+    CU_TRY(c, cudaMemcpyAsync(d_off.p, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    L.sample_off = d_off.as<uint64_t>();
+  }
+  CU_TRY(c, cudaMemcpyAsync(d_samples.p, samples, total * 4, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  uint64_t tot = 0;
+  rc = encode_pipeline(c, FRONT_DEGA, d_samples.as<float>(), L, max_len, params, d_payload.as<uint8_t>(), payload_cap,
+                       d_bits.as<uint64_t>(), d_boff.as<uint64_t>(), d_status.as<int32_t>(), &tot);
+  if (total_bytes)
+    *total_bytes = tot;
+  if (rc != DC_OK && rc != DC_ERR_MEMORY)
+    return rc;
+  if (bit_len)
+    CU_TRY(c, cudaMemcpyAsync(bit_len, d_bits.p, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (byte_off)
+    CU_TRY(c, cudaMemcpyAsync(byte_off, d_boff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (status)
+    CU_TRY(c, cudaMemcpyAsync(status, d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (rc == DC_OK && payload && tot)
+    CU_TRY(c, cudaMemcpyAsync(payload, d_payload.p, tot, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  return rc;
+}
+
+int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_bytes, const uint64_t *bit_len, const uint64_t *byte_off,
+                        const dc_layout *layout, const dc_params *params, float *samples, uint64_t *n_out, int32_t *status)
+{
+  if (!c || !params_ok(params) || !layout || !bit_len || !byte_off)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  Layout L;
+  uint64_t max_len, total;
+  int rc = make_layout(c, layout, layout->sample_off, L, max_len, total);
+  if (rc != DC_OK)
+    return rc;
+  const uint64_t n = L.n_streams;
+  DevBuf d_samples, d_off, d_payload, d_bits, d_boff, d_status, d_nout;
+  if ((rc = d_samples.alloc(c, total * 4)) || (rc = d_payload.alloc(c, round_up(payload_bytes, 4) + 16)) || (rc = d_bits.alloc(c, n * 8)) ||
+      (rc = d_boff.alloc(c, (n + 1) * 8)) || (rc = d_status.alloc(c, n * 4)) || (rc = d_nout.alloc(c, n * 8)))
+    return rc;
+  if (layout->sample_off)
+  {
+    if ((rc = d_off.alloc(c, (n + 1) * 8)))
+      return rc;
+    CU_TRY(c, cudaMemcpyAsync(d_off.p, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    L.sample_off = d_off.as<uint64_t>();
+  }
+  CU_TRY(c, cudaMemcpyAsync(d_payload.p, payload, payload_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemcpyAsync(d_bits.p, bit_len, n * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemcpyAsync(d_boff.p, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  rc = decode_pipeline(c, FRONT_DEGA, d_payload.as<uint8_t>(), d_bits.as<uint64_t>(), d_boff.as<uint64_t>(), L, max_len, params,
+                       d_samples.as<float>(), d_nout.as<uint64_t>(), d_status.as<int32_t>());
+  if (rc != DC_OK)
+    return rc;
+  if (samples && total)
+    CU_TRY(c, cudaMemcpyAsync(samples, d_samples.p, total * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (n_out)
+    CU_TRY(c, cudaMemcpyAsync(n_out, d_nout.p, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (status)
+    CU_TRY(c, cudaMemcpyAsync(status, d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_err(c, "kernel execution failed: %s", cudaGetErrorString(e));
+    return DC_ERR_LIBRARY_CALL;
+  }
+  return DC_OK;
+}
+
+// ---- plugin face: one stage over one stream ---------------------------------------------------------------
+uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *p)
+{
+  const uint64_t vs = p ? p->value_size_bits : 32;
+  switch (stage)
+  {
+    case DC_STAGE_NORMALIZE: return (in_bits / 32 * vs + 7) / 8 + 8;
+    case DC_STAGE_DENORMALIZE: return in_bits / vs * 4 + 8;
+    case DC_STAGE_DIFF_ENC:
+    case DC_STAGE_DIFF_DEC: return (in_bits + 7) / 8 + 8;
+    case DC_STAGE_SEG_ENC: return (in_bits / vs * (2 * vs + 1) + 7) / 8 + 8;
+    case DC_STAGE_SEG_DEC: return (in_bits * vs + 7) / 8 + 8;
+    case DC_STAGE_BAC_ENC: return (in_bits * 13 / 8 + 7) / 8 + 64;
+    case DC_STAGE_BAC_DEC: return in_bits * 4 + 4096;    /* first guess; dc_stage_run_host reports the exact need on overflow */
+    case DC_STAGE_LZMH_ENC: return (in_bits / 8 * 10 + 7) / 8 + 8;
+    case DC_STAGE_LZMH_DEC: return in_bits / 10 * 274 / 2 + 4096;
+    case DC_STAGE_DEGA_ENC: return (in_bits / 32 * (2 * vs + 1) * 13 / 8 + 7) / 8 + 64;
+    case DC_STAGE_DEGA_DEC: return in_bits * 16 + 4096;
+    default: return 0;
+  }
+}
+
+int dc_lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_bits);
+
+int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits, const dc_params *params, uint8_t *out, uint64_t out_cap,
+                      uint64_t *out_bits)
+{
+  if (!c || !params_ok(params) || !out_bits || stage < 0 || stage >= DC_STAGE_COUNT)
+    return DC_ERR_INVALID_VALUE;
+  *out_bits = 0;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  if (stage == DC_STAGE_LZMH_ENC || stage == DC_STAGE_LZMH_DEC)
+    return dc_lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_bits, out, out_cap, out_bits);
+
+  const uint32_t vs = params->value_size_bits;
+  const uint64_t in_bytes = (in_bits + 7) / 8;
+  const bool float_in = stage == DC_STAGE_NORMALIZE || stage == DC_STAGE_DEGA_ENC;
+  const bool float_out = stage == DC_STAGE_DENORMALIZE || stage == DC_STAGE_DEGA_DEC;
+  const uint64_t n_in = float_in ? in_bits / 32 : in_bits / vs;   // values in (front-end stages)
+
+  // single-stream geometry; all scratch strides are per-stream capacities
+  Layout L;
+  L.n_streams = 1;
+  L.channel_len = n_in;
+  L.block_len = n_in ? n_in : 1;
+  L.blocks_per_channel = 1;
+  L.sample_off = nullptr;
+
+  uint64_t mid_cap = 0, out_cap_dev = 0;   // bytes
+  for (unsigned boost = 1;; boost *= 8)
+  {
+    switch (stage)
+    {
+      case DC_STAGE_NORMALIZE:
+      case DC_STAGE_DIFF_ENC:
+      case DC_STAGE_DIFF_DEC: out_cap_dev = fixed_cap_bytes(std::max(n_in, in_bits / vs + 1), vs); break;
+      case DC_STAGE_SEG_ENC: out_cap_dev = seg_cap_bytes(n_in, vs); break;
+      case DC_STAGE_SEG_DEC: out_cap_dev = fixed_cap_bytes(in_bits + 1, vs); break;
+      case DC_STAGE_DENORMALIZE: out_cap_dev = round_up((in_bits / vs + 1) * 4, 16); break;
+      case DC_STAGE_BAC_ENC: out_cap_dev = bac_cap_bytes(round_up(in_bytes + 8, 16), params->adaptive, boost); break;
+      case DC_STAGE_BAC_DEC: out_cap_dev = round_up((in_bytes * 4 + 4096) * boost, 16); break;
+      case DC_STAGE_DEGA_ENC:
+        mid_cap = seg_cap_bytes(n_in, vs);
+        out_cap_dev = bac_cap_bytes(mid_cap, params->adaptive, boost);
+        break;
+      case DC_STAGE_DEGA_DEC:
+        mid_cap = round_up((in_bytes * 4 + 4096) * boost, 16);
+        out_cap_dev = 0;   // sized after the coder reports the SEG bit count
+        break;
+      default: return DC_ERR_INVALID_VALUE;
+    }
+    // DEGA decode needs the sample capacity: every SEG code word is at least one bit long
+    const uint64_t dega_dec_samples = mid_cap * 8;
+    if (stage == DC_STAGE_DEGA_DEC)
+      out_cap_dev = round_up(dega_dec_samples * 4 + 16, 16);
+
+    const uint64_t need = Bump::size_of(round_up(in_bytes, 16) + 32, 1) + Bump::size_of(mid_cap, 1) + Bump::size_of(out_cap_dev, 1) +
+                          Bump::size_of(8, 8) + 4096;
+    int rc = arena_reserve(c, need);
+    if (rc != DC_OK)
+      return rc;
+    Bump b(c->arena);
+    uint8_t *d_in = b.take<uint8_t>(round_up(in_bytes, 16) + 32);
+    uint8_t *d_mid = b.take<uint8_t>(mid_cap);
+    uint8_t *d_out = b.take<uint8_t>(out_cap_dev);
+    uint64_t *d_meta = b.take<uint64_t>(8);   // [0]=in_bits [1]=mid_bits [2]=out_bits [3]=n_out [4]=status(int32) [5]=overflow flag
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_meta + 4);
+
+    CU_TRY(c, cudaMemsetAsync(d_meta, 0, 8 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemsetAsync(d_in + (in_bytes & ~(uint64_t)15), 0, 32, c->stream), DC_ERR_LIBRARY_CALL);
+    if (in_bytes)
+      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(d_meta, &in_bits, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+
+    BitSrc src_in;
+    src_in.base = d_in;
+    src_in.byte_off = nullptr;
+    src_in.stride_bytes = 0;
+    src_in.nbits = d_meta + 0;
+
+    const bool is_front = stage == DC_STAGE_NORMALIZE || stage == DC_STAGE_DIFF_ENC || stage == DC_STAGE_SEG_ENC || stage == DC_STAGE_DEGA_ENC;
+    const bool is_back = stage == DC_STAGE_DENORMALIZE || stage == DC_STAGE_DIFF_DEC || stage == DC_STAGE_SEG_DEC || stage == DC_STAGE_DEGA_DEC;
+
+    if (is_front)
+    {
+      FrontArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.lay = L;
+      fa.samples = reinterpret_cast<const float *>(d_in);
+      fa.in = src_in;
+      fa.in_is_float = float_in;
+      fa.do_norm = float_in;
+      fa.do_diff = stage == DC_STAGE_DIFF_ENC || stage == DC_STAGE_DEGA_ENC;
+      fa.out_seg = stage == DC_STAGE_SEG_ENC || stage == DC_STAGE_DEGA_ENC;
+      fa.vs = vs;
+      fa.nf = params->normalization_factor;
+      fa.out.base = stage == DC_STAGE_DEGA_ENC ? d_mid : d_out;
+      fa.out.stride_bytes = stage == DC_STAGE_DEGA_ENC ? mid_cap : out_cap_dev;
+      fa.out.nbits = stage == DC_STAGE_DEGA_ENC ? d_meta + 1 : d_meta + 2;
+      fa.status = d_status;
+      launch_front(fa, c->stream);
+    }
+    if (stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC)
+    {
+      BacArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.n_streams = 1;
+      if (stage == DC_STAGE_BAC_ENC)
+        ba.in = src_in;
+      else
+      {
+        ba.in.base = d_mid;
+        ba.in.byte_off = nullptr;
+        ba.in.stride_bytes = mid_cap;
+        ba.in.nbits = d_meta + 1;
+      }
+      ba.out.base = d_out;
+      ba.out.stride_bytes = out_cap_dev;
+      ba.out.nbits = d_meta + 2;
+      ba.adaptive = params->adaptive;
+      ba.div_table = c->d_div;
+      ba.status = d_status;
+      ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_meta + 5);
+      launch_bac_encode(ba, c->stream);
+    }
+    if (stage == DC_STAGE_BAC_DEC || stage == DC_STAGE_DEGA_DEC)
+    {
+      BacArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.n_streams = 1;
+      ba.in = src_in;
+      ba.out.base = stage == DC_STAGE_BAC_DEC ? d_out : d_mid;
+      ba.out.stride_bytes = stage == DC_STAGE_BAC_DEC ? out_cap_dev : mid_cap;
+      ba.out.nbits = stage == DC_STAGE_BAC_DEC ? d_meta + 2 : d_meta + 1;
+      ba.adaptive = params->adaptive;
+      ba.div_table = c->d_div;
+      ba.status = d_status;
+      ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_meta + 5);
+      launch_bac_decode(ba, c->stream);
+    }
+    if (is_back)
+    {
+      BackArgs ka;
+      memset(&ka, 0, sizeof(ka));
+      Layout LO = L;
+      const uint64_t cap_samples = stage == DC_STAGE_DEGA_DEC ? dega_dec_samples : in_bits / vs + 1;
+      LO.channel_len = cap_samples;
+      LO.block_len = cap_samples;
+      ka.lay = LO;
+      ka.n_streams = 1;
+      if (stage == DC_STAGE_DEGA_DEC)
+      {
+        ka.in.base = d_mid;
+        ka.in.byte_off = nullptr;
+        ka.in.stride_bytes = mid_cap;
+        ka.in.nbits = d_meta + 1;
+      }
+      else
+        ka.in = src_in;
+      ka.in_seg = stage == DC_STAGE_SEG_DEC || stage == DC_STAGE_DEGA_DEC;
+      ka.do_undiff = stage == DC_STAGE_DIFF_DEC || stage == DC_STAGE_DEGA_DEC;
+      ka.do_denorm = float_out;
+      ka.vs = vs;
+      ka.nf = params->normalization_factor;
+      ka.samples = reinterpret_cast<float *>(d_out);
+      ka.out.base = d_out;
+      ka.out.stride_bytes = out_cap_dev;
+      ka.out.nbits = d_meta + 2;
+      ka.n_out = d_meta + 3;
+      ka.status = d_status;
+      launch_back(ka, c->stream);
+    }
+    if ((rc = check_launch(c, "stage kernels")) != DC_OK)
+      return rc;
+    uint64_t meta[8];
+    if ((rc = read_back(c, d_meta, meta, 8)) != DC_OK)
+      return rc;
+    const int32_t st = (int32_t)(meta[4] & 0xFFFFFFFFu);
+    if (meta[5] != 0 && boost < 4096)
+      continue;   // coder scratch too small: retry with a larger stride
+    if (st != 0)
+      return st;
+    uint64_t bits = float_out ? meta[3] * 32 : meta[2];
+    if (float_in && (in_bits % 32) != 0)
+      return DC_ERR_LIBRARY_CALL;   // short read of the last float (io_macros.h:13-27)
+    *out_bits = bits;
+    const uint64_t nbytes = (bits + 7) / 8;
+    if (nbytes > out_cap)
+    {
+      set_err(c, "stage output needs %llu bytes, capacity is %llu", (unsigned long long)nbytes, (unsigned long long)out_cap);
+      return DC_ERR_MEMORY;
+    }
+    if (nbytes)
+    {
+      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+    }
+    return DC_OK;
+  }
+}
+
+}  // extern "C"

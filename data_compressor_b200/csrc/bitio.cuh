@@ -1,0 +1,239 @@
+// bitio.cuh -- device-side bit streams with the DCIOLib layout.
+//
+// DCIOLib packs bits MSB-first into bytes (DCIOLib/src/bit_file_buffer.c:183,244) and multi-bit values
+// big-endian across bytes (bit_file_buffer.c:297-308).  Every bit stream that leaves a kernel is stored in
+// exactly that byte order, so a stream can be handed to the reference (or to the next kernel) as plain
+// bytes.  Kernels work on 32-bit words: word k of a stream holds stream bits [32k, 32k+32) and is stored
+// byte-swapped (PRMT) so that memory order == stream order.
+#pragma once
+
+#include <stdint.h>
+
+namespace dc {
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// A set of per-stream bit strings in one allocation.
+//   byte_off != nullptr : stream s starts at base + byte_off[s] (densely packed payload, any alignment)
+//   byte_off == nullptr : stream s starts at base + s * stride_bytes (scratch, stride multiple of 16)
+struct BitSrc
+{
+  const uint8_t *base;
+  const uint64_t *byte_off;
+  uint64_t stride_bytes;
+  const uint64_t *nbits;
+};
+
+struct BitDst
+{
+  uint8_t *base;
+  uint64_t stride_bytes;   // per-stream capacity, multiple of 16
+  uint64_t *nbits;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Writer: private to one thread, appends MSB-first.  Capacity overflow is recorded, never written.
+struct BitWriter
+{
+  uint32_t *words;
+  uint32_t cap_words;
+  uint32_t nwords;
+  uint32_t nacc;     // pending bits in acc, always < 32 between calls
+  uint64_t acc;      // low nacc bits are pending
+  bool overflow;
+
+  __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes)
+  {
+    words = reinterpret_cast<uint32_t *>(p);
+    cap_words = (uint32_t)(cap_bytes >> 2);
+    nwords = 0;
+    nacc = 0;
+    acc = 0;
+    overflow = false;
+  }
+
+  __device__ __forceinline__ void flush_word()
+  {
+    nacc -= 32;
+    const uint32_t w = (uint32_t)(acc >> nacc);
+    if (nwords < cap_words)
+      words[nwords] = bswap32(w);
+    else
+      overflow = true;
+    nwords++;
+  }
+
+  // n in [0, 32], v < 2^n
+  __device__ __forceinline__ void put(uint32_t v, uint32_t n)
+  {
+    acc = (acc << n) | v;
+    nacc += n;
+    if (nacc >= 32)
+      flush_word();
+  }
+
+  // n in [0, 64], v < 2^n
+  __device__ __forceinline__ void put64(uint64_t v, uint32_t n)
+  {
+    if (n > 32)
+    {
+      put((uint32_t)(v >> 32), n - 32);
+      put((uint32_t)v, 32);
+    }
+    else
+      put((uint32_t)v, n);
+  }
+
+  __device__ __forceinline__ void zeros(uint32_t n)
+  {
+    while (n > 32)
+    {
+      put(0u, 32);
+      n -= 32;
+    }
+    put(0u, n);
+  }
+
+  // n copies of `bit` (n unbounded)
+  __device__ __forceinline__ void run(uint32_t bit, uint64_t n)
+  {
+    const uint32_t pat = bit ? 0xFFFFFFFFu : 0u;
+    while (n >= 32)
+    {
+      put(pat, 32);
+      n -= 32;
+    }
+    if (n)
+      put(pat >> (32 - (uint32_t)n), (uint32_t)n);
+  }
+
+  __device__ __forceinline__ uint64_t bits() const { return (uint64_t)nwords * 32 + nacc; }
+
+  // Flushes the fractional word (left aligned, zero padded); returns the exact bit count.
+  __device__ __forceinline__ uint64_t finish()
+  {
+    const uint64_t total = bits();
+    if (nacc)
+    {
+      const uint32_t w = (uint32_t)(acc << (32 - nacc));
+      if (nwords < cap_words)
+        words[nwords] = bswap32(w);
+      else
+        overflow = true;
+    }
+    return total;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Reader: private to one thread.  The stream may start at any byte address; bits past `nbits` read as 0
+// (the stream that follows in a dense payload is masked off).
+struct BitReader
+{
+  const uint32_t *words;   // 4-byte aligned base
+  uint32_t phase;          // 0, 8, 16, 24: bit offset of the stream inside words[0]
+  uint64_t nbits;
+  uint64_t pos;            // bits consumed
+  uint64_t win;            // MSB-aligned look-ahead
+  uint32_t wn;             // bits held in win
+  uint32_t next;           // next 32-bit chunk to fetch
+  uint32_t carry;          // BE(words[next]) when phase != 0
+
+  __device__ __forceinline__ void init(const uint8_t *p, uint64_t nbits_)
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    phase = (uint32_t)(a & 3) * 8;
+    nbits = nbits_;
+    pos = 0;
+    win = 0;
+    wn = 0;
+    next = 0;
+    carry = 0;
+    if (phase != 0 && nbits != 0)
+      carry = bswap32(__ldg(words));
+  }
+
+  // stream bits [32k, 32k+32), zero beyond nbits; k must be fetched in increasing order
+  __device__ __forceinline__ uint32_t fetch32()
+  {
+    const uint64_t bitpos = (uint64_t)next * 32;
+    uint32_t w = 0;
+    if (bitpos < nbits)
+    {
+      const uint64_t remaining = nbits - bitpos;
+      if (phase == 0)
+        w = bswap32(__ldg(words + next));
+      else
+      {
+        uint32_t nx = 0;
+        if (remaining > 32 - phase)            // the chunk really extends into the next aligned word
+          nx = bswap32(__ldg(words + next + 1));
+        w = __funnelshift_l(nx, carry, phase);
+        carry = nx;
+      }
+      if (remaining < 32)
+        w &= ~(0xFFFFFFFFu >> (uint32_t)remaining);
+    }
+    next++;
+    return w;
+  }
+
+  __device__ __forceinline__ void refill()
+  {
+    if (wn <= 32)
+    {
+      win |= (uint64_t)fetch32() << (32 - wn);
+      wn += 32;
+    }
+  }
+
+  __device__ __forceinline__ uint64_t avail() const { return pos < nbits ? nbits - pos : 0; }
+  __device__ __forceinline__ bool eof() const { return pos >= nbits; }
+
+  // n in [0, 32]; bits past the end read as zero, pos keeps counting
+  __device__ __forceinline__ uint32_t take(uint32_t n)
+  {
+    refill();
+    const uint32_t v = n ? (uint32_t)(win >> (64 - n)) : 0u;
+    win <<= n;
+    wn -= n;
+    pos += n;
+    return v;
+  }
+
+  // n in [0, 64]
+  __device__ __forceinline__ uint64_t take64(uint32_t n)
+  {
+    if (n > 32)
+    {
+      const uint64_t hi = take(n - 32);
+      return (hi << 32) | take(32);
+    }
+    return take(n);
+  }
+
+  // look at the next 32 bits without consuming
+  __device__ __forceinline__ uint32_t peek32()
+  {
+    refill();
+    return (uint32_t)(win >> 32);
+  }
+};
+
+__device__ __forceinline__ const uint8_t *src_ptr(const BitSrc &s, uint64_t i)
+{
+  return s.base + (s.byte_off ? s.byte_off[i] : i * s.stride_bytes);
+}
+
+__device__ __forceinline__ uint8_t *dst_ptr(const BitDst &d, uint64_t i) { return d.base + i * d.stride_bytes; }
+
+// sign extension of the low vs bits (EXTEND_IO_INT_SIGN, DCLib/inc/io_macros.h:89-90)
+__device__ __forceinline__ int64_t sext(uint64_t v, uint32_t vs)
+{
+  return vs == 64 ? (int64_t)v : ((int64_t)(v << (64 - vs)) >> (64 - vs));
+}
+
+__device__ __forceinline__ uint64_t low_mask(uint32_t vs) { return vs == 64 ? ~0ull : ((1ull << vs) - 1); }
+
+}  // namespace dc

@@ -1,0 +1,300 @@
+// dega_kernels.cu -- sm_100a kernels of the DEGA chain (normalize -> diff -> seg -> bac) and its inverse.
+//
+// Work decomposition: one independent stream (= one reference invocation, see include/dc_cuda.h) per thread.
+// The arithmetic coder is inherently sequential per stream (bac.c:152-162), so parallelism comes from the
+// number of streams; the kernels are integer-issue bound, not HBM bound.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dega_device.cuh"
+
+namespace dc {
+
+static uint64_t g_launches = 0;
+uint64_t launch_counter() { return g_launches; }
+
+__global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
+{
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.lay.n_streams)
+    front_body(a, s);
+}
+
+void launch_front(const FrontArgs &a, cudaStream_t st)
+{
+  if (a.lay.n_streams == 0)
+    return;
+  const unsigned block = 128;
+  const unsigned grid = (unsigned)((a.lay.n_streams + block - 1) / block);
+  front_kernel<<<grid, block, 0, st>>>(a);
+  g_launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
+{
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.n_streams)
+    back_body(a, s);
+}
+
+void launch_back(const BackArgs &a, cudaStream_t st)
+{
+  if (a.n_streams == 0)
+    return;
+  const unsigned block = 128;
+  const unsigned grid = (unsigned)((a.n_streams + block - 1) / block);
+  back_kernel<<<grid, block, 0, st>>>(a);
+  g_launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Arithmetic coder kernels.  The 128 KiB division table lives in shared memory (one copy per CTA, one CTA of
+// kBacThreads threads per SM); before the first halving every lane of a warp has coded the same number of
+// symbols, so `total` is warp-uniform and the table read is a broadcast.
+static const int kBacThreads = 1024;
+
+int bac_smem_bytes() { return kDivTableEntries * (int)sizeof(DivEntry); }
+
+__device__ __forceinline__ void load_div_table(DivEntry *smem, const DivEntry *gmem)
+{
+  const uint4 *g = reinterpret_cast<const uint4 *>(gmem);
+  uint4 *d = reinterpret_cast<uint4 *>(smem);
+  for (int i = threadIdx.x; i < kDivTableEntries / 2; i += blockDim.x)
+    d[i] = __ldg(g + i);
+  __syncthreads();
+}
+
+template <bool ADAPTIVE>
+__global__ void __launch_bounds__(kBacThreads, 1) bac_encode_kernel(const BacArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
+  load_div_table(tab, a.div_table);
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.n_streams)
+    bac_encode_body<ADAPTIVE>(a, s, tab);
+}
+
+template <bool ADAPTIVE>
+__global__ void __launch_bounds__(kBacThreads, 1) bac_decode_kernel(const BacArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
+  load_div_table(tab, a.div_table);
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.n_streams)
+    bac_decode_body<ADAPTIVE>(a, s, tab);
+}
+
+template <typename K>
+static void launch_bac(K kernel, const BacArgs &a, cudaStream_t st)
+{
+  if (a.n_streams == 0)
+    return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bac_smem_bytes());
+  const unsigned grid = (unsigned)((a.n_streams + kBacThreads - 1) / kBacThreads);
+  kernel<<<grid, kBacThreads, bac_smem_bytes(), st>>>(a);
+  g_launches++;
+}
+
+void launch_bac_encode(const BacArgs &a, cudaStream_t st)
+{
+  if (a.adaptive)
+    launch_bac(bac_encode_kernel<true>, a, st);
+  else
+    launch_bac(bac_encode_kernel<false>, a, st);
+}
+
+void launch_bac_decode(const BacArgs &a, cudaStream_t st)
+{
+  if (a.adaptive)
+    launch_bac(bac_decode_kernel<true>, a, st);
+  else
+    launch_bac(bac_decode_kernel<false>, a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Compaction: device-wide exclusive prefix sum over the per-stream byte counts, then a gather into the dense
+// payload.  Three small kernels: tile-local scan (4096 streams per CTA), scan of the tile totals, add-back.
+static const int kScanThreads = 1024;
+static const int kScanItems = 4;
+static const int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *warp_sums, uint64_t &block_total)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+  {
+    const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d)
+      inc += t;
+  }
+  if (lane == 31)
+    warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0)
+  {
+    uint64_t ws = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, ws, d);
+      if (lane >= d)
+        ws += t;
+    }
+    warp_sums[lane] = ws;   // inclusive
+  }
+  __syncthreads();
+  const uint64_t warp_base = wid ? warp_sums[wid - 1] : 0;
+  block_total = warp_sums[(blockDim.x >> 5) - 1];
+  return warp_base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const uint64_t *nbits, uint64_t n, uint64_t *byte_off,
+                                                                  uint64_t *tile_sums)
+{
+  __shared__ uint64_t warp_sums[32];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint64_t v[kScanItems];
+  uint64_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+  {
+    const uint64_t i = base + k;
+    v[k] = i < n ? (nbits[i] + 7) >> 3 : 0;
+    sum += v[k];
+  }
+  uint64_t total;
+  uint64_t run = block_exclusive_scan(sum, warp_sums, total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+  {
+    const uint64_t i = base + k;
+    if (i < n)
+      byte_off[i] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 0)
+    tile_sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of the tile totals in place; tile_sums[n_tiles] receives the grand total
+__global__ void __launch_bounds__(kScanThreads) scan_totals_kernel(uint64_t *tile_sums, uint64_t n_tiles)
+{
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0)
+    carry_s = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n_tiles; base += kScanThreads)
+  {
+    const uint64_t i = base + threadIdx.x;
+    const uint64_t v = i < n_tiles ? tile_sums[i] : 0;
+    uint64_t total;
+    const uint64_t ex = block_exclusive_scan(v, warp_sums, total);
+    const uint64_t carry = carry_s;
+    if (i < n_tiles)
+      tile_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    tile_sums[n_tiles] = carry_s;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint64_t *byte_off, uint64_t n, const uint64_t *tile_sums,
+                                                                uint64_t n_tiles)
+{
+  const uint64_t add = tile_sums[blockIdx.x];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+  {
+    const uint64_t i = base + k;
+    if (i < n)
+      byte_off[i] += add;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    byte_off[n] = tile_sums[n_tiles];
+}
+
+void launch_byte_scan(const uint64_t *nbits, uint64_t n, uint64_t *byte_off, uint64_t *tile_tmp, cudaStream_t st)
+{
+  const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  if (n == 0)
+  {
+    cudaMemsetAsync(byte_off, 0, sizeof(uint64_t), st);
+    return;
+  }
+  scan_tiles_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(nbits, n, byte_off, tile_tmp);
+  scan_totals_kernel<<<1, kScanThreads, 0, st>>>(tile_tmp, n_tiles);
+  scan_add_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(byte_off, n, tile_tmp, n_tiles);
+  g_launches += 3;
+}
+
+// one warp per stream, byte-granular destination
+__global__ void __launch_bounds__(256) gather_kernel(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t *nbits,
+                                                     const uint64_t *byte_off, uint64_t n, uint8_t *payload,
+                                                     uint64_t payload_cap)
+{
+  const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (s >= n)
+    return;
+  const uint64_t nbytes = (nbits[s] + 7) >> 3;
+  const uint64_t off = byte_off[s];
+  if (off + nbytes > payload_cap)
+    return;
+  const uint8_t *src = scratch + s * stride_bytes;
+  uint8_t *dst = payload + off;
+  // head bytes up to 4-byte alignment of dst, then words assembled from the (aligned) source, then the tail
+  const uint64_t head = min((uint64_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), nbytes);
+  if (lane < head)
+    dst[lane] = src[lane];
+  const uint64_t nwords = (nbytes - head) >> 2;
+  const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src);
+  uint32_t *dst_w = reinterpret_cast<uint32_t *>(dst + head);
+  const uint32_t sh = (uint32_t)head * 8;   // source words are read shifted by `head` bytes (little-endian memory)
+  for (uint64_t k = lane; k < nwords; k += 32)
+  {
+    const uint32_t a = src_w[k];
+    const uint32_t v = sh ? __funnelshift_r(a, src_w[k + 1], sh) : a;
+    dst_w[k] = v;
+  }
+  const uint64_t done = head + nwords * 4;
+  if (done + lane < nbytes)
+    dst[done + lane] = src[done + lane];
+}
+
+void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t *nbits, const uint64_t *byte_off, uint64_t n,
+                   uint8_t *payload, uint64_t payload_cap, cudaStream_t st)
+{
+  if (n == 0)
+    return;
+  const unsigned block = 256;
+  const unsigned grid = (unsigned)((n * 32 + block - 1) / block);
+  gather_kernel<<<grid, block, 0, st>>>(scratch, stride_bytes, nbits, byte_off, n, payload, payload_cap);
+  g_launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void build_div_table(DivEntry *t)
+{
+  t[0].m = 0;
+  t[0].l = 0;
+  for (uint32_t d = 1; d < (uint32_t)kDivTableEntries; d++)
+  {
+    uint32_t l = 0;
+    while ((1u << l) < d)
+      l++;
+    t[d].m = (uint32_t)((((uint64_t)1 << (30 + l)) + d - 1) / d);
+    t[d].l = l;
+  }
+}
+
+}  // namespace dc

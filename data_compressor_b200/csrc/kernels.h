@@ -1,0 +1,124 @@
+// kernels.h -- host-callable launch wrappers of the sm_100a kernels (internal; the public ABI is include/dc_cuda.h)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bitio.cuh"
+
+namespace dc {
+
+// Stream geometry inside one flat sample array (see dc_layout in include/dc_cuda.h)
+struct Layout
+{
+  uint64_t n_streams;
+  uint64_t channel_len;
+  uint64_t block_len;            // uniform mode: samples per block (>= 1)
+  uint64_t blocks_per_channel;   // uniform mode
+  const uint64_t *sample_off;    // ragged mode (device pointer) or nullptr
+};
+
+__host__ __device__ inline void stream_extent(const Layout &L, uint64_t s, uint64_t &off, uint64_t &len)
+{
+  if (L.sample_off)
+  {
+    off = L.sample_off[s];
+    len = L.sample_off[s + 1] - off;
+  }
+  else
+  {
+    const uint64_t c = s / L.blocks_per_channel;
+    const uint64_t b = s - c * L.blocks_per_channel;
+    const uint64_t start = b * L.block_len;
+    off = c * L.channel_len + start;
+    len = L.channel_len - start < L.block_len ? L.channel_len - start : L.block_len;
+  }
+}
+
+// Division table for the arithmetic coder: entry d = {m, l} with floor(x / d) == umulhi(x << 2, m) >> l for
+// every x < 2^30 (exact, Granlund-Montgomery round-up).  16384 entries, entries 0..1 unused.
+struct DivEntry
+{
+  uint32_t m;
+  uint32_t l;
+};
+static const int kDivTableEntries = 16384;
+void build_div_table(DivEntry *host_table);
+
+// ---- front end: [normalize] -> [diff] -> {seg | fixed-width pack} ---------------------------------
+struct FrontArgs
+{
+  Layout lay;
+  const float *samples;     // float source (in_is_float)
+  BitSrc in;                // vs-bit integer source (!in_is_float)
+  int in_is_float;
+  int do_norm;
+  int do_diff;
+  int out_seg;              // 1: signed Exp-Golomb, 0: vs-bit fields
+  uint32_t vs;
+  float nf;
+  BitDst out;
+  int32_t *status;
+};
+void launch_front(const FrontArgs &a, cudaStream_t st);
+
+// ---- back end: {seg parse | fixed-width unpack} -> [undiff] -> [denormalize] ------------------------
+struct BackArgs
+{
+  Layout lay;               // destination geometry for float output (capacity per stream)
+  uint64_t n_streams;
+  BitSrc in;
+  int in_seg;
+  int do_undiff;
+  int do_denorm;            // 1: float32 out into `samples`, 0: vs-bit fields into `out`
+  uint32_t vs;
+  float nf;
+  float *samples;
+  BitDst out;
+  uint64_t *n_out;          // values produced per stream
+  int32_t *status;
+};
+void launch_back(const BackArgs &a, cudaStream_t st);
+
+// ---- binary arithmetic coder -----------------------------------------------------------------------
+struct BacArgs
+{
+  uint64_t n_streams;
+  BitSrc in;
+  BitDst out;
+  int adaptive;
+  const DivEntry *div_table;   // device copy
+  int32_t *status;             // in/out: streams with status != 0 are skipped (out bits = 0)
+  unsigned long long *overflow_flag;   // set to 1 when any stream outgrew its output stride (may be nullptr)
+};
+void launch_bac_encode(const BacArgs &a, cudaStream_t st);
+void launch_bac_decode(const BacArgs &a, cudaStream_t st);
+int bac_smem_bytes();
+
+// ---- compaction: byte counts -> exclusive scan -> dense payload ---------------------------------------
+// byte_off[n+1] = exclusive scan of ceil(nbits[s] / 8); tile_tmp needs ceil(n / 4096) + 1 uint64.
+void launch_byte_scan(const uint64_t *nbits, uint64_t n, uint64_t *byte_off, uint64_t *tile_tmp, cudaStream_t st);
+// copies stream s (scratch, fixed stride) to payload + byte_off[s]; streams that do not fit are skipped
+void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t *nbits, const uint64_t *byte_off,
+                   uint64_t n, uint8_t *payload, uint64_t payload_cap, cudaStream_t st);
+
+// ---- LZMH ------------------------------------------------------------------------------------------------
+struct LzmhArgs
+{
+  uint64_t n_streams;
+  const uint8_t *in;
+  const uint64_t *in_off;      // [n+1] byte offsets (encode) / nullptr
+  BitSrc bits_in;              // decode input
+  BitDst bits_out;             // encode output
+  uint8_t *out;                // decode output bytes
+  const uint64_t *out_off;     // [n+1] capacity windows (decode)
+  uint64_t *out_len;           // decode: bytes produced
+  int32_t *status;
+};
+void launch_lzmh_encode(const LzmhArgs &a, cudaStream_t st);
+void launch_lzmh_decode(const LzmhArgs &a, cudaStream_t st);
+
+// number of kernel launches issued so far by the launch_* wrappers (process-wide)
+uint64_t launch_counter();
+
+}  // namespace dc

@@ -1,0 +1,154 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# golden vectors (tests/golden/golden.npz, produced from the real reference by tests/golden/make_golden.py)
+class Golden:
+    def __init__(self):
+        here = os.path.join(ROOT, "tests", "golden")
+        self.z = np.load(os.path.join(here, "golden.npz"))
+        self.testfile = np.load(os.path.join(here, "testfile_f32.npy"))
+        self.names = [str(n) for n in self.z["names"]]
+
+    def get(self, name):
+        z = self.z
+        in_bits, vs, adaptive, rc, out_bits = (int(v) for v in z[f"{name}/meta"])
+        inp = z[f"{name}/input"]
+        if inp.size == 0 and in_bits == self.testfile.size * 32:
+            inp = self.testfile.view(np.uint8)
+        return dict(name=name, input=inp, in_bits=in_bits, chain=[int(c) for c in z[f"{name}/chain"]], vs=vs,
+                    nf=float(z[f"{name}/nf"][0]), adaptive=adaptive, rc=rc, out_bits=out_bits, out=z[f"{name}/out"],
+                    sha256=bytes(z[f"{name}/sha256"]).decode())
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import binding
+    binding.build(ref=False)
+    return binding.Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The real reference (oracle/_ref).  Present in the build container; on the GPU box only if it travelled."""
+    from oracle import binding
+    if os.path.isdir("/root/reference/DataCompressor"):
+        binding.build(ref=True)
+    if not binding.Ref.available():
+        pytest.skip("oracle/_ref/libdcref.so not available")
+    return binding.Ref()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-compiled device bodies (tests/host_sim): logic tests without a GPU
+class Sim:
+    def __init__(self):
+        d = os.path.join(ROOT, "tests", "host_sim")
+        so = os.path.join(d, "_build", "libdcsim.so")
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        srcs = [os.path.join(d, "sim.cpp"), os.path.join(d, "host_shim.h")] + \
+            [os.path.join(ROOT, "data_compressor_b200", "csrc", f) for f in ("bitio.cuh", "bac.cuh", "dega_device.cuh", "kernels.h",
+                                                                             "lzmh_device.cuh")]
+        srcs = [s for s in srcs if os.path.exists(s)]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+            subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+                            "-Wno-maybe-uninitialized", "-I", cuda_inc, "-o", so, os.path.join(d, "sim.cpp")], check=True)
+        L = C.CDLL(so)
+        L.sim_stage_run.restype = C.c_int
+        L.sim_stage_run.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_float, C.c_int, C.c_void_p, C.c_uint64,
+                                    C.POINTER(C.c_uint64)]
+        L.sim_check_div_table.restype = C.c_uint64
+        L.sim_check_div_table.argtypes = [C.c_uint32]
+        L.sim_dega_encode_batch.restype = C.c_int
+        L.sim_dega_encode_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float, C.c_int, C.c_void_p,
+                                            C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.sim_dega_decode_batch.restype = C.c_int
+        L.sim_dega_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float,
+                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib = L
+
+    def stage_run(self, stage, data, nbits=None, vs=32, nf=100.0, adaptive=0, cap=None):
+        src = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        if nbits is None:
+            nbits = src.size * 8
+        cap = cap or max(1 << 16, src.size * 40 + 4096)
+        out = np.zeros(cap, dtype=np.uint8)
+        ob = C.c_uint64(0)
+        rc = self.lib.sim_stage_run(stage, src.ctypes.data if src.size else None, nbits, vs, nf, int(adaptive), out.ctypes.data, cap,
+                                    C.byref(ob))
+        nb = int(ob.value) if rc == 0 else 0
+        return rc, out[: (nb + 7) // 8].tobytes(), nb
+
+    def dega_encode_batch(self, x, block_len, vs=32, nf=100.0, adaptive=1):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        nc, cl = x.shape
+        bl = block_len or max(cl, 1)
+        n = nc * (1 if cl == 0 else (cl + bl - 1) // bl)
+        cap = x.size * 9 + n * 16 + 64
+        payload = np.zeros(cap, np.uint8)
+        bit_len = np.zeros(n, np.uint64)
+        byte_off = np.zeros(n + 1, np.uint64)
+        status = np.zeros(n, np.int32)
+        total = C.c_uint64(0)
+        rc = self.lib.sim_dega_encode_batch(x.ctypes.data, nc, cl, block_len, vs, nf, int(adaptive), payload.ctypes.data, cap,
+                                            bit_len.ctypes.data, byte_off.ctypes.data, status.ctypes.data, C.byref(total))
+        return rc, payload[: total.value], bit_len, byte_off, status
+
+    def dega_decode_batch(self, payload, bit_len, byte_off, nc, cl, block_len, vs=32, nf=100.0, adaptive=1):
+        payload = np.ascontiguousarray(payload, np.uint8)
+        n = bit_len.size
+        out = np.zeros((nc, cl), np.float32)
+        n_out = np.zeros(n, np.uint64)
+        status = np.zeros(n, np.int32)
+        rc = self.lib.sim_dega_decode_batch(payload.ctypes.data, bit_len.ctypes.data, byte_off.ctypes.data, nc, cl, block_len, vs, nf,
+                                            int(adaptive), out.ctypes.data, n_out.ctypes.data, status.ctypes.data)
+        return rc, out, n_out, status
+
+
+@pytest.fixture(scope="session")
+def sim():
+    return Sim()
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="session")
+def ctx():
+    """A live dc_ctx on cuda:0 (GPU tests only).  Fails -- never skips -- when the extension is missing."""
+    import torch
+    assert torch.cuda.is_available(), "GPU test running without a GPU"
+    from data_compressor_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def split_streams(x, block_len):
+    """(channel, block) streams of a [n_channels, channel_len] array, in container order."""
+    nc, cl = x.shape
+    bl = block_len or max(cl, 1)
+    out = []
+    for c in range(nc):
+        for b in range(0, max(cl, 1), bl):
+            out.append(x[c, b:b + bl])
+    return out

@@ -1,0 +1,322 @@
+// sim.cpp -- host-compiled copy of the kernels' per-thread bodies, for logic tests without a GPU.
+// TEST HARNESS ONLY (see host_shim.h).  Mirrors dc_stage_run_host() for one stream and the batch DEGA
+// encode/decode for uniform layouts, using plain host memory instead of device buffers.
+#include "host_shim.h"
+
+#include <algorithm>
+#include <vector>
+
+#include "../../data_compressor_b200/csrc/dega_device.cuh"
+#include "../../include/dc_cuda.h"
+
+using namespace dc;
+
+namespace dc {
+void build_div_table(DivEntry *t)
+{
+  t[0].m = 0;
+  t[0].l = 0;
+  for (uint32_t d = 1; d < (uint32_t)kDivTableEntries; d++)
+  {
+    uint32_t l = 0;
+    while ((1u << l) < d)
+      l++;
+    t[d].m = (uint32_t)((((uint64_t)1 << (30 + l)) + d - 1) / d);
+    t[d].l = l;
+  }
+}
+}  // namespace dc
+
+static const DivEntry *div_table()
+{
+  static std::vector<DivEntry> tab;
+  if (tab.empty())
+  {
+    tab.resize(kDivTableEntries);
+    build_div_table(tab.data());
+  }
+  return tab.data();
+}
+
+static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+// exhaustive-ish check of the division table: returns the number of mismatches
+uint64_t sim_check_div_table(uint32_t stride)
+{
+  const DivEntry *t = div_table();
+  uint64_t bad = 0;
+  for (uint32_t d = 1; d < (uint32_t)kDivTableEntries; d++)
+  {
+    for (uint64_t x = 0; x < (1ull << 30); x += stride)
+      bad += div_magic((uint32_t)x, t[d]) != (uint32_t)(x / d);
+    const uint64_t edge[] = { (1ull << 30) - 1, (1ull << 29), (1ull << 29) - 1, 65536ull * 8192, 65535ull * 8191 };
+    for (uint64_t x : edge)
+      bad += div_magic((uint32_t)x, t[d]) != (uint32_t)(x / d);
+    for (uint64_t k = 1; k * d < (1ull << 30); k += 1 + stride / 64)   // multiples of d and their predecessors
+    {
+      bad += div_magic((uint32_t)(k * d), t[d]) != (uint32_t)k;
+      bad += div_magic((uint32_t)(k * d - 1), t[d]) != (uint32_t)(k - 1);
+    }
+  }
+  return bad;
+}
+
+// Same contract as dc_stage_run_host (include/dc_cuda.h), executed by the host-compiled device bodies.
+int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, float nf, int adaptive, uint8_t *out, uint64_t out_cap,
+                  uint64_t *out_bits)
+{
+  *out_bits = 0;
+  const uint64_t in_bytes = (in_bits + 7) / 8;
+  const bool float_in = stage == DC_STAGE_NORMALIZE || stage == DC_STAGE_DEGA_ENC;
+  const bool float_out = stage == DC_STAGE_DENORMALIZE || stage == DC_STAGE_DEGA_DEC;
+  const uint64_t n_in = float_in ? in_bits / 32 : in_bits / vs;
+
+  std::vector<uint8_t> h_in(round_up(in_bytes, 16) + 64, 0);
+  if (in_bytes)
+    memcpy(h_in.data(), in, in_bytes);
+  uint64_t meta[8] = { in_bits, 0, 0, 0, 0, 0, 0, 0 };
+  int32_t *status = reinterpret_cast<int32_t *>(&meta[4]);
+
+  Layout L;
+  L.n_streams = 1;
+  L.channel_len = n_in;
+  L.block_len = n_in ? n_in : 1;
+  L.blocks_per_channel = 1;
+  L.sample_off = nullptr;
+
+  BitSrc src_in = { h_in.data(), nullptr, 0, &meta[0] };
+  for (unsigned boost = 1;; boost *= 8)
+  {
+    uint64_t mid_cap = 0, out_dev = 0;
+    const uint64_t seg_cap = round_up((n_in * (2ull * vs + 1) + 7) / 8 + 8, 16);
+    switch (stage)
+    {
+      case DC_STAGE_NORMALIZE:
+      case DC_STAGE_DIFF_ENC:
+      case DC_STAGE_DIFF_DEC: out_dev = round_up((std::max(n_in, in_bits / vs + 1) * vs + 7) / 8 + 8, 16); break;
+      case DC_STAGE_SEG_ENC: out_dev = seg_cap; break;
+      case DC_STAGE_SEG_DEC: out_dev = round_up(((in_bits + 1) * vs + 7) / 8 + 8, 16); break;
+      case DC_STAGE_DENORMALIZE: out_dev = round_up((in_bits / vs + 1) * 4, 16); break;
+      case DC_STAGE_BAC_ENC: out_dev = round_up((in_bytes + 24) * 13 / 8 * boost + 64, 16); break;
+      case DC_STAGE_BAC_DEC: out_dev = round_up((in_bytes * 4 + 4096) * boost, 16); break;
+      case DC_STAGE_DEGA_ENC: mid_cap = seg_cap; out_dev = round_up(seg_cap * 13 / 8 * boost + 64, 16); break;
+      case DC_STAGE_DEGA_DEC: mid_cap = round_up((in_bytes * 4 + 4096) * boost, 16); out_dev = round_up(mid_cap * 8 * 4 + 16, 16); break;
+      default: return DC_ERR_INVALID_VALUE;
+    }
+    std::vector<uint8_t> h_mid(mid_cap + 16, 0), h_out(out_dev + 16, 0);
+    memset(meta + 1, 0, 7 * sizeof(uint64_t));
+
+    const bool is_front = stage == DC_STAGE_NORMALIZE || stage == DC_STAGE_DIFF_ENC || stage == DC_STAGE_SEG_ENC || stage == DC_STAGE_DEGA_ENC;
+    const bool is_back = stage == DC_STAGE_DENORMALIZE || stage == DC_STAGE_DIFF_DEC || stage == DC_STAGE_SEG_DEC || stage == DC_STAGE_DEGA_DEC;
+    if (is_front)
+    {
+      FrontArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.lay = L;
+      fa.samples = reinterpret_cast<const float *>(h_in.data());
+      fa.in = src_in;
+      fa.in_is_float = float_in;
+      fa.do_norm = float_in;
+      fa.do_diff = stage == DC_STAGE_DIFF_ENC || stage == DC_STAGE_DEGA_ENC;
+      fa.out_seg = stage == DC_STAGE_SEG_ENC || stage == DC_STAGE_DEGA_ENC;
+      fa.vs = vs;
+      fa.nf = nf;
+      fa.out.base = stage == DC_STAGE_DEGA_ENC ? h_mid.data() : h_out.data();
+      fa.out.stride_bytes = stage == DC_STAGE_DEGA_ENC ? mid_cap : out_dev;
+      fa.out.nbits = stage == DC_STAGE_DEGA_ENC ? &meta[1] : &meta[2];
+      fa.status = status;
+      front_body(fa, 0);
+    }
+    if (stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC || stage == DC_STAGE_BAC_DEC || stage == DC_STAGE_DEGA_DEC)
+    {
+      const bool enc = stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC;
+      BacArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.n_streams = 1;
+      if (stage == DC_STAGE_DEGA_ENC)
+        ba.in = BitSrc{ h_mid.data(), nullptr, mid_cap, &meta[1] };
+      else
+        ba.in = src_in;
+      const bool to_mid = stage == DC_STAGE_DEGA_DEC;
+      ba.out.base = to_mid ? h_mid.data() : h_out.data();
+      ba.out.stride_bytes = to_mid ? mid_cap : out_dev;
+      ba.out.nbits = to_mid ? &meta[1] : &meta[2];
+      ba.adaptive = adaptive;
+      ba.div_table = div_table();
+      ba.status = status;
+      ba.overflow_flag = reinterpret_cast<unsigned long long *>(&meta[5]);
+      if (enc)
+      {
+        if (adaptive)
+          bac_encode_body<true>(ba, 0, div_table());
+        else
+          bac_encode_body<false>(ba, 0, div_table());
+      }
+      else
+      {
+        if (adaptive)
+          bac_decode_body<true>(ba, 0, div_table());
+        else
+          bac_decode_body<false>(ba, 0, div_table());
+      }
+    }
+    if (is_back)
+    {
+      BackArgs ka;
+      memset(&ka, 0, sizeof(ka));
+      Layout LO = L;
+      const uint64_t cap_samples = stage == DC_STAGE_DEGA_DEC ? mid_cap * 8 : in_bits / vs + 1;
+      LO.channel_len = cap_samples;
+      LO.block_len = cap_samples;
+      ka.lay = LO;
+      ka.n_streams = 1;
+      if (stage == DC_STAGE_DEGA_DEC)
+        ka.in = BitSrc{ h_mid.data(), nullptr, mid_cap, &meta[1] };
+      else
+        ka.in = src_in;
+      ka.in_seg = stage == DC_STAGE_SEG_DEC || stage == DC_STAGE_DEGA_DEC;
+      ka.do_undiff = stage == DC_STAGE_DIFF_DEC || stage == DC_STAGE_DEGA_DEC;
+      ka.do_denorm = float_out;
+      ka.vs = vs;
+      ka.nf = nf;
+      ka.samples = reinterpret_cast<float *>(h_out.data());
+      ka.out.base = h_out.data();
+      ka.out.stride_bytes = out_dev;
+      ka.out.nbits = &meta[2];
+      ka.n_out = &meta[3];
+      ka.status = status;
+      back_body(ka, 0);
+    }
+    if (meta[5] != 0 && boost < 4096)
+      continue;
+    if (*status != 0)
+      return *status;
+    const uint64_t bits = float_out ? meta[3] * 32 : meta[2];
+    if (float_in && (in_bits % 32) != 0)
+      return DC_ERR_LIBRARY_CALL;
+    *out_bits = bits;
+    const uint64_t nbytes = (bits + 7) / 8;
+    if (nbytes > out_cap)
+      return DC_ERR_MEMORY;
+    if (nbytes)
+      memcpy(out, h_out.data(), nbytes);
+    return DC_OK;
+  }
+}
+
+// Batch DEGA encode over a uniform layout on host memory; writes per-stream payloads back to back (dense) the way
+// scan + gather do.  Returns 0 or the first negative code; status/bit_len/byte_off as in dc_dega_encode_device.
+int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t channel_len, uint64_t block_len, uint32_t vs, float nf,
+                          int adaptive, uint8_t *payload, uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status,
+                          uint64_t *total_bytes)
+{
+  Layout L;
+  const uint64_t bl = block_len == 0 ? std::max<uint64_t>(channel_len, 1) : block_len;
+  L.blocks_per_channel = channel_len == 0 ? 1 : (channel_len + bl - 1) / bl;
+  L.n_streams = n_channels * L.blocks_per_channel;
+  L.channel_len = channel_len;
+  L.block_len = bl;
+  L.sample_off = nullptr;
+  const uint64_t n = L.n_streams;
+  const uint64_t max_len = std::min(bl, channel_len);
+  const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
+  const uint64_t bac_cap = round_up(seg_cap * 13 / 8 + 64, 16);
+  std::vector<uint8_t> seg(n * seg_cap + 16), bac(n * bac_cap + 16);
+  std::vector<uint64_t> seg_bits(n);
+  unsigned long long flag = 0;
+  for (uint64_t s = 0; s < n; s++)
+    status[s] = 0;
+  FrontArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.lay = L;
+  fa.samples = samples;
+  fa.in_is_float = fa.do_norm = fa.do_diff = fa.out_seg = 1;
+  fa.vs = vs;
+  fa.nf = nf;
+  fa.out = BitDst{ seg.data(), seg_cap, seg_bits.data() };
+  fa.status = status;
+  BacArgs ba;
+  memset(&ba, 0, sizeof(ba));
+  ba.n_streams = n;
+  ba.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data() };
+  ba.out = BitDst{ bac.data(), bac_cap, bit_len };
+  ba.adaptive = adaptive;
+  ba.div_table = div_table();
+  ba.status = status;
+  ba.overflow_flag = &flag;
+  uint64_t run = 0;
+  for (uint64_t s = 0; s < n; s++)
+  {
+    front_body(fa, s);
+    if (adaptive)
+      bac_encode_body<true>(ba, s, div_table());
+    else
+      bac_encode_body<false>(ba, s, div_table());
+    byte_off[s] = run;
+    const uint64_t nb = (bit_len[s] + 7) / 8;
+    if (run + nb <= payload_cap)
+      memcpy(payload + run, bac.data() + s * bac_cap, nb);
+    run += nb;
+  }
+  byte_off[n] = run;
+  *total_bytes = run;
+  if (flag)
+    return DC_ERR_MEMORY;
+  return run > payload_cap ? DC_ERR_MEMORY : DC_OK;
+}
+
+int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const uint64_t *byte_off, uint64_t n_channels,
+                          uint64_t channel_len, uint64_t block_len, uint32_t vs, float nf, int adaptive, float *samples, uint64_t *n_out,
+                          int32_t *status)
+{
+  Layout L;
+  const uint64_t bl = block_len == 0 ? std::max<uint64_t>(channel_len, 1) : block_len;
+  L.blocks_per_channel = channel_len == 0 ? 1 : (channel_len + bl - 1) / bl;
+  L.n_streams = n_channels * L.blocks_per_channel;
+  L.channel_len = channel_len;
+  L.block_len = bl;
+  L.sample_off = nullptr;
+  const uint64_t n = L.n_streams;
+  const uint64_t max_len = std::min(bl, channel_len);
+  const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
+  std::vector<uint8_t> seg(n * seg_cap + 16);
+  std::vector<uint64_t> seg_bits(n);
+  // the payload is copied into a padded buffer: the reader may touch the aligned word after the last byte
+  std::vector<uint8_t> pay(byte_off[n] + 16, 0);
+  memcpy(pay.data(), payload, byte_off[n]);
+  unsigned long long flag = 0;
+  for (uint64_t s = 0; s < n; s++)
+    status[s] = 0;
+  BacArgs ba;
+  memset(&ba, 0, sizeof(ba));
+  ba.n_streams = n;
+  ba.in = BitSrc{ pay.data(), byte_off, 0, bit_len };
+  ba.out = BitDst{ seg.data(), seg_cap, seg_bits.data() };
+  ba.adaptive = adaptive;
+  ba.div_table = div_table();
+  ba.status = status;
+  ba.overflow_flag = &flag;
+  BackArgs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.lay = L;
+  ka.n_streams = n;
+  ka.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data() };
+  ka.in_seg = ka.do_undiff = ka.do_denorm = 1;
+  ka.vs = vs;
+  ka.nf = nf;
+  ka.samples = samples;
+  ka.n_out = n_out;
+  ka.status = status;
+  for (uint64_t s = 0; s < n; s++)
+  {
+    if (adaptive)
+      bac_decode_body<true>(ba, s, div_table());
+    else
+      bac_decode_body<false>(ba, s, div_table());
+    back_body(ka, s);
+  }
+  return DC_OK;
+}
+}

@@ -1,0 +1,202 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (include/dc_cuda.h), against the oracle and
+the committed golden vectors.  Bit-exact everywhere (integer/byte work; the two float32 steps use IEEE
+round-to-nearest intrinsics and are compared bit for bit as well)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import split_streams
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+DEGA_ENC, DEGA_DEC = 10, 11
+
+
+def profile(rng, shape, step=200, base=30000):
+    k = np.abs(np.cumsum(rng.integers(-step, step + 1, shape), axis=-1) + base)
+    return (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+
+
+# ---- plugin face: one stage, one stream ----------------------------------------------------------------------
+def test_golden_vectors_stage_by_stage(ctx, golden):
+    """Every golden chain, one GPU stage at a time (what DCCLI's stage loop would do with GPU plugins)."""
+    for name in golden.names:
+        g = golden.get(name)
+        if any(s in (ob.LZMH_ENC, ob.LZMH_DEC) for s in g["chain"]):
+            continue
+        data, nbits, rc = g["input"].tobytes(), g["in_bits"], 0
+        for st in g["chain"]:
+            rc, data, nbits = ctx.stage_run(st, data, nbits, g["vs"], g["nf"], g["adaptive"])
+            if rc != 0:
+                break
+        assert rc == g["rc"], name
+        if rc == 0:
+            assert nbits == g["out_bits"], name
+            if g["out"].size:
+                assert data == g["out"].tobytes(), name
+
+
+def test_make_test_on_gpu(ctx, golden):
+    """The reference's `make test`: DEGA round trip of testdata/input.txt, plus the exact compressed bytes."""
+    g = golden.get("testfile_stage4")
+    rc, out, nb = ctx.stage_run(DEGA_ENC, golden.testfile, None, 32, 100.0, True)
+    assert rc == 0 and nb == 1354613 and out == g["out"].tobytes()
+    rc, dec, nb2 = ctx.stage_run(DEGA_DEC, out, nb, 32, 100.0, True)
+    assert rc == 0 and nb2 == 3200000 and dec == golden.testfile.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_stage_chains_vs_oracle(ctx, oracle, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(0, 4000))
+    x = profile(rng, n, step=int(rng.choice([3, 300, 30000])))
+    vs = int(rng.choice([22, 24, 32, 33, 48, 64]))
+    ad = int(rng.integers(0, 2))
+    data, nbits = x.tobytes(), n * 32
+    for st in ob.DEGA_ENC + ob.DEGA_DEC:
+        want = oracle.run_chain([st], data, nbits, vs, 100.0, ad)
+        got = ctx.stage_run(st, data, nbits, vs, 100.0, ad)
+        assert got == want, (st, vs, ad, n)
+        data, nbits = got[1], got[2]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_bac_random_bits(ctx, oracle, seed):
+    rng = np.random.default_rng(50 + seed)
+    n = int(rng.choice([0, 1, 33, 1000, 20000, 70000]))
+    p1 = float(rng.choice([0.001, 0.1, 0.5, 0.97]))
+    bits = np.packbits((rng.random(n) < p1).astype(np.uint8))
+    for ad in (0, 1):
+        want = oracle.run_chain([ob.BAC_ENC], bits, n, adaptive=ad)
+        got = ctx.stage_run(ob.BAC_ENC, bits, n, adaptive=ad)
+        assert got == want
+        assert ctx.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad) == oracle.run_chain([ob.BAC_DEC], got[1], got[2], adaptive=ad)
+
+
+def test_garbage_and_truncated_inputs(ctx, oracle):
+    rng = np.random.default_rng(9)
+    junk = rng.integers(0, 256, 300, dtype=np.uint8)
+    for nbits in (1, 15, 16, 17, 333, 2400):
+        for st, kw in ((ob.SEG_DEC, dict(vs=32)), (ob.SEG_DEC, dict(vs=8)), (ob.BAC_DEC, dict(adaptive=1)), (ob.BAC_DEC, dict(adaptive=0))):
+            a = ctx.stage_run(st, junk, nbits, **kw)
+            b = oracle.run_chain([st], junk, nbits, **kw)
+            assert a[0] == b[0] and (a[0] != 0 or a == b), (st, nbits, kw)
+
+
+# ---- batch face --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("block_len", [0, 1, 7, 64, 1000])
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_batch_encode_matches_oracle_per_stream(ctx, oracle, block_len, adaptive):
+    rng = np.random.default_rng(block_len + 17)
+    nc, cl = 37, 333
+    x = profile(rng, (nc, cl))
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=block_len, adaptive=adaptive)
+    bit_len = enc.bit_len.cpu().numpy()
+    byte_off = enc.byte_off.cpu().numpy()
+    payload = enc.payload[: enc.total_bytes].cpu().numpy()
+    assert not enc.status.any().item()
+    streams = split_streams(x, block_len)
+    assert len(streams) == bit_len.size
+    for s, xs in enumerate(streams):
+        rc, ob_, nb = oracle.dega_encode(xs, adaptive=int(adaptive))
+        assert rc == 0 and nb == bit_len[s], s
+        o = int(byte_off[s])
+        assert payload[o:o + len(ob_)].tobytes() == ob_, s
+        assert int(byte_off[s + 1]) - o == len(ob_)
+    assert int(byte_off[-1]) == enc.total_bytes
+    y, n_out, status = ctx.dega_decode(enc, adaptive=adaptive)
+    assert not status.any().item()
+    assert torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
+    assert n_out.cpu().tolist() == [len(s) for s in streams]
+
+
+@pytest.mark.parametrize("vs", [17, 24, 40, 64])
+def test_batch_value_sizes(ctx, oracle, vs):
+    rng = np.random.default_rng(vs)
+    x = profile(rng, (9, 500), step=50, base=2000)
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=128, vs=vs)
+    streams = split_streams(x, 128)
+    for s, xs in enumerate(streams):
+        assert enc.stream_bytes(s) == oracle.dega_encode(xs, vs=vs)[1]
+    y, n_out, status = ctx.dega_decode(enc, vs=vs)
+    assert torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
+
+
+def test_batch_failed_streams_are_isolated(ctx, oracle):
+    x = np.full((4, 50), 12.5, dtype=np.float32)
+    x[1, 20] = -3.0            # diff rejects
+    x[3, 0] = 3.0e9            # normalize rejects (a-1)
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda())
+    assert enc.status.cpu().tolist() == [0, -1, 0, -1]
+    assert enc.bit_len.cpu().tolist()[1] == 0 and enc.bit_len.cpu().tolist()[3] == 0
+    assert enc.stream_bytes(0) == oracle.dega_encode(x[0])[1]
+    assert enc.stream_bytes(2) == oracle.dega_encode(x[2])[1]
+
+
+def test_empty_and_tiny_batches(ctx, oracle):
+    enc = ctx.dega_encode(torch.zeros((3, 0), dtype=torch.float32, device="cuda"))
+    assert enc.bit_len.cpu().tolist() == [3, 3, 3] and enc.total_bytes == 3          # empty stream -> 3 bits `001`
+    assert enc.stream_bytes(1) == bytes([0x20])
+    enc = ctx.dega_encode(torch.tensor([[1.0, 2.0, 1.5]], device="cuda"))
+    assert enc.stream_bytes(0) == bytes.fromhex("f9c008475e84") and int(enc.bit_len[0]) == 47
+
+
+def test_host_buffer_face(ctx, oracle):
+    rng = np.random.default_rng(3)
+    x = profile(rng, (11, 700))
+    payload, bit_len, byte_off, status = ctx.dega_encode_host(x, block_len=256)
+    streams = split_streams(x, 256)
+    for s, xs in enumerate(streams):
+        o = int(byte_off[s])
+        want = oracle.dega_encode(xs)[1]
+        assert payload[o:o + len(want)].tobytes() == want
+    y, n_out, status = ctx.dega_decode_host(payload, bit_len, byte_off, 11, 700, 256)
+    assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not status.any()
+
+
+def test_axdr_normalize_only(ctx, oracle):
+    rng = np.random.default_rng(5)
+    x = profile(rng, (50, 96), step=40, base=500)
+    for vs in (17, 24, 32):
+        enc = ctx.axdr_encode(torch.from_numpy(x).cuda(), vs=vs)
+        for s in (0, 7, 49):
+            want = oracle.run_chain([ob.NORMALIZE], x[s], 96 * 32, vs)
+            assert int(enc.bit_len[s]) == want[2] and enc.stream_bytes(s) == want[1]
+        y, n_out, status = ctx.axdr_decode(enc, vs=vs)
+        assert torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
+
+
+# ---- full size: BASELINE.json config 2 (4096 channels x 1 day), size-independent properties ------------------
+def test_full_size_round_trip_and_spot_checks(ctx, oracle):
+    from data_compressor_b200 import synth
+    nc, cl, bl = 4096, 86400, 1024
+    x = synth.redd_like(nc, cl, device="cuda")
+    enc = ctx.dega_encode(x, block_len=bl)
+    assert not enc.status.any().item()
+    n = enc.n_streams
+    assert n == nc * 85
+    # container invariants: offsets are the exclusive scan of the byte counts
+    nbytes = (enc.bit_len + 7) // 8
+    assert torch.equal(enc.byte_off[1:], torch.cumsum(nbytes, 0)) and int(enc.byte_off[0]) == 0
+    assert enc.total_bytes == int(enc.byte_off[-1])
+    ratio = x.numel() * 4 / enc.total_bytes
+    assert 2.0 < ratio < 4.0
+    # lossless round trip of all 353,894,400 samples
+    y, n_out, status = ctx.dega_decode(enc)
+    assert not status.any().item()
+    assert torch.equal(y.view(torch.int32), x.view(torch.int32))
+    del y
+    # spot-check 24 random (channel, block) streams bit for bit against the oracle
+    rng = np.random.default_rng(0)
+    for s in rng.integers(0, n, 24):
+        c, b = divmod(int(s), 85)
+        xs = x[c, b * bl:(b + 1) * bl].cpu().numpy()
+        rc, want, nb = oracle.dega_encode(xs)
+        assert rc == 0 and nb == int(enc.bit_len[s]) and enc.stream_bytes(int(s)) == want
+    # whole-channel streams (parity with one plain DCCLI run per channel), on a slice
+    enc2 = ctx.dega_encode(x[:64].contiguous(), block_len=0)
+    rc, want, nb = oracle.dega_encode(x[5].cpu().numpy())
+    assert enc2.stream_bytes(5) == want and int(enc2.bit_len[5]) == nb
+    y2, _, _ = ctx.dega_decode(enc2)
+    assert torch.equal(y2.view(torch.int32), x[:64].view(torch.int32))

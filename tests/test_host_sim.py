@@ -1,0 +1,132 @@
+"""Logic tests of the kernels' per-thread bodies, compiled for the host by tests/host_sim (no GPU needed).
+
+This is the same source that nvcc compiles for sm_100a (data_compressor_b200/csrc/*.cuh); the harness is test-only
+and is not a fallback path.  The GPU-side parity tests proper are in test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import split_streams
+from oracle import binding as ob
+
+# enum dc_stage == enum dco_stage_id for the ten plain stages; 10/11 are the fused DEGA chains
+DEGA_ENC, DEGA_DEC = 10, 11
+
+
+def test_division_table_is_exact(sim):
+    assert sim.lib.sim_check_div_table(65521) == 0
+
+
+def test_every_golden_vector_stage_by_stage(sim, golden):
+    """Runs each golden chain one stage at a time through the device bodies, like DCCLI's stage loop."""
+    for name in golden.names:
+        g = golden.get(name)
+        if any(s in (ob.LZMH_ENC, ob.LZMH_DEC) for s in g["chain"]):
+            continue
+        data, nbits, rc = g["input"].tobytes(), g["in_bits"], 0
+        for st in g["chain"]:
+            rc, data, nbits = sim.stage_run(st, data, nbits, g["vs"], g["nf"], g["adaptive"])
+            if rc != 0:
+                break
+        assert rc == g["rc"], name
+        if rc == 0:
+            assert nbits == g["out_bits"], name
+            if g["out"].size:
+                assert data == g["out"].tobytes(), name
+
+
+def test_fused_dega_matches_golden(sim, golden):
+    g = golden.get("testfile_stage4")
+    rc, out, nb = sim.stage_run(DEGA_ENC, golden.testfile, None, 32, 100.0, 1)
+    assert rc == 0 and nb == g["out_bits"] and out == g["out"].tobytes()
+    rc, dec, nb2 = sim.stage_run(DEGA_DEC, out, nb, 32, 100.0, 1, cap=golden.testfile.size * 4 + 64)
+    assert rc == 0 and dec == golden.testfile.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_streams_vs_oracle(sim, oracle, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(0, 3000))
+    k = np.abs(np.cumsum(rng.integers(-int(rng.choice([3, 300, 30000])), 301, n)) + 20000)
+    x = (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+    vs = int(rng.choice([22, 24, 32, 33, 48, 64]))
+    ad = int(rng.integers(0, 2))
+    want = oracle.run_chain(ob.DEGA_ENC, x, n * 32, vs, 100.0, ad)
+    got = sim.stage_run(DEGA_ENC, x, n * 32, vs, 100.0, ad)
+    assert got == want
+    back = sim.stage_run(DEGA_DEC, got[1], got[2], vs, 100.0, ad, cap=n * 4 + 64)
+    assert back == oracle.run_chain(ob.DEGA_DEC, got[1], got[2], vs, 100.0, ad)
+    if k.size == 0 or k.max() < (1 << 21):     # float32 round trip is only exact for moderate magnitudes
+        assert back[1] == x.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_bac_random_bits_vs_oracle(sim, oracle, seed):
+    rng = np.random.default_rng(50 + seed)
+    n = int(rng.choice([0, 1, 2, 31, 32, 33, 1000, 20000, 70000]))
+    p1 = float(rng.choice([0.001, 0.1, 0.5, 0.97]))
+    bits = np.packbits((rng.random(n) < p1).astype(np.uint8))
+    for ad in (0, 1):
+        want = oracle.run_chain([ob.BAC_ENC], bits, n, adaptive=ad)
+        got = sim.stage_run(ob.BAC_ENC, bits, n, adaptive=ad)
+        assert got == want
+        assert sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad) == oracle.run_chain([ob.BAC_DEC], got[1], got[2], adaptive=ad)
+        # the decoder reading the byte-padded file sees 8 * nbytes bits
+        assert sim.stage_run(ob.BAC_DEC, got[1], len(got[1]) * 8, adaptive=ad) == \
+            oracle.run_chain([ob.BAC_DEC], got[1], len(got[1]) * 8, adaptive=ad)
+
+
+def test_bac_long_runs_force_halvings_and_pending_bits(sim, oracle):
+    # 200k symbols: > 20 halvings; alternating blocks produce long E3 (pending) runs
+    rng = np.random.default_rng(7)
+    bits = np.concatenate([np.zeros(60000, np.uint8), (rng.random(80000) < 0.5).astype(np.uint8), np.ones(60000, np.uint8)])
+    packed = np.packbits(bits)
+    want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=1)
+    got = sim.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=1)
+    assert got == want
+    assert sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=1)[1] == packed.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_garbage_decoders_vs_oracle(sim, oracle, seed):
+    rng = np.random.default_rng(90 + seed)
+    junk = rng.integers(0, 256, 300, dtype=np.uint8)
+    nbits = int(rng.integers(1, 2400))
+    for vs in (8, 17, 32, 64):
+        a = sim.stage_run(ob.SEG_DEC, junk, nbits, vs)
+        b = oracle.run_chain([ob.SEG_DEC], junk, nbits, vs)
+        assert a[0] == b[0] and (a[0] != 0 or a == b)
+    for ad in (0, 1):
+        a = sim.stage_run(ob.BAC_DEC, junk, nbits, adaptive=ad)
+        b = oracle.run_chain([ob.BAC_DEC], junk, nbits, adaptive=ad)
+        assert a[0] == b[0] and (a[0] != 0 or a == b)
+
+
+@pytest.mark.parametrize("block_len", [0, 1, 7, 64, 1000])
+def test_batch_layout_and_dense_payload(sim, oracle, block_len):
+    """(channel, block) streams, ragged last block, dense byte-aligned payload, unaligned decode reads."""
+    rng = np.random.default_rng(block_len)
+    nc, cl = 5, 333
+    k = np.abs(np.cumsum(rng.integers(-200, 201, (nc, cl)), axis=1) + 30000)
+    x = (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+    rc, payload, bit_len, byte_off, status = sim.dega_encode_batch(x, block_len)
+    assert rc == 0 and not status.any()
+    streams = split_streams(x, block_len)
+    assert len(streams) == bit_len.size
+    for s, xs in enumerate(streams):
+        orc, obytes, obits = oracle.dega_encode(xs)
+        assert orc == 0 and obits == bit_len[s]
+        o = int(byte_off[s])
+        assert payload[o:o + len(obytes)].tobytes() == obytes
+        assert int(byte_off[s + 1]) - o == len(obytes)
+    rc, y, n_out, status = sim.dega_decode_batch(payload, bit_len, byte_off, nc, cl, block_len)
+    assert rc == 0 and not status.any()
+    assert np.array_equal(y.view(np.uint32), x.view(np.uint32))
+    assert [int(v) for v in n_out] == [len(s) for s in streams]
+
+
+def test_batch_failed_stream_is_isolated(sim, oracle):
+    x = np.full((3, 50), 12.5, dtype=np.float32)
+    x[1, 20] = -3.0           # negative sample: diff reads it unsigned and rejects
+    rc, payload, bit_len, byte_off, status = sim.dega_encode_batch(x, 0)
+    assert list(status) == [0, -1, 0] and bit_len[1] == 0
+    assert payload[int(byte_off[2]):].tobytes() == oracle.dega_encode(x[2])[1]

@@ -1,0 +1,83 @@
+"""Randomised parity of the oracle against the REAL reference (oracle/_ref, compiled from /root/reference).
+Skipped where the reference build is absent."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+
+
+def rand_profile(rng, n, scale=300.0, neg=False):
+    k = np.cumsum(rng.integers(-300, 301, n)) + int(scale * 100)
+    k = np.abs(k) if not neg else k
+    return (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dega_chain_random(oracle, ref, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 5000))
+    x = rand_profile(rng, n)
+    vs = int(rng.choice([20, 24, 32, 40, 64]))
+    ad = int(rng.integers(0, 2))
+    for k in range(1, 5):
+        chain = ob.DEGA_ENC[:k]
+        assert oracle.run_chain(chain, x, n * 32, vs, 100.0, ad) == ref.run_chain(chain, x, n * 32, vs, 100.0, ad)
+    rc, pay, nb = oracle.dega_encode(x, vs, 100.0, ad)
+    for k in range(1, 5):
+        chain = ob.DEGA_DEC[:k]
+        assert oracle.run_chain(chain, pay, nb, vs, 100.0, ad) == ref.run_chain(chain, pay, nb, vs, 100.0, ad)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_error_codes_random(oracle, ref, seed):
+    rng = np.random.default_rng(100 + seed)
+    x = rand_profile(rng, 200, neg=True)
+    x[int(rng.integers(0, 200))] = np.float32(rng.choice([-5.0, 1e9, -1e12, 400000.0]))
+    for vs in (16, 24, 32):
+        for k in range(1, 5):
+            a = oracle.run_chain(ob.DEGA_ENC[:k], x, None, vs, 100.0, 1)
+            b = ref.run_chain(ob.DEGA_ENC[:k], x, None, vs, 100.0, 1)
+            assert a[0] == b[0] and (a[0] != 0 or a == b)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_bac_random_bits(oracle, ref, seed):
+    rng = np.random.default_rng(200 + seed)
+    n = int(rng.integers(0, 60000))
+    p1 = float(rng.choice([0.01, 0.2, 0.5, 0.9]))
+    bits = np.packbits((rng.random(n) < p1).astype(np.uint8))
+    for ad in (0, 1):
+        a = oracle.run_chain([ob.BAC_ENC], bits, n, adaptive=ad)
+        assert a == ref.run_chain([ob.BAC_ENC], bits, n, adaptive=ad)
+        assert oracle.run_chain([ob.BAC_DEC], a[1], a[2], adaptive=ad) == ref.run_chain([ob.BAC_DEC], a[1], a[2], adaptive=ad)
+        # garbage in: both must agree on the error / output as well
+        junk = rng.integers(0, 256, 64, dtype=np.uint8)
+        assert oracle.run_chain([ob.BAC_DEC], junk, adaptive=ad)[0] == ref.run_chain([ob.BAC_DEC], junk, adaptive=ad)[0]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_seg_decode_garbage(oracle, ref, seed):
+    rng = np.random.default_rng(300 + seed)
+    junk = rng.integers(0, 256, 200, dtype=np.uint8)
+    nbits = int(rng.integers(1, 1600))
+    for vs in (8, 17, 32, 64):
+        a = oracle.run_chain([ob.SEG_DEC], junk, nbits, vs)
+        b = ref.run_chain([ob.SEG_DEC], junk, nbits, vs)
+        assert a[0] == b[0] and (a[0] != 0 or a == b)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lzmh_random(oracle, ref, seed):
+    rng = np.random.default_rng(400 + seed)
+    n = int(rng.choice([0, 1, 2, 3, 127, 128, 129, 274, 275, 402, 403, 404, 1000, 5000]))
+    kind = seed % 3
+    if kind == 0:
+        data = rng.integers(0, 4, n, dtype=np.uint8)                       # highly repetitive
+    elif kind == 1:
+        data = np.frombuffer(("".join(f"{v:.2f}\n" for v in rng.random(n // 5 + 1) * 300))[:n].encode(), dtype=np.uint8)
+    else:
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+    a = oracle.run_chain([ob.LZMH_ENC], data, data.size * 8)
+    b = ref.run_chain([ob.LZMH_ENC], data, data.size * 8)
+    assert a == b
+    assert oracle.run_chain([ob.LZMH_DEC], a[1], a[2]) == ref.run_chain([ob.LZMH_DEC], a[1], a[2])
