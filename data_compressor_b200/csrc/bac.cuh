@@ -2,23 +2,28 @@
 //
 // The reference is the Witten/Neal/Cleary coder with RANGE_BITS = 16 over the three symbols {0, 1, EOF}
 // (bac.c:13,29-31).  This restatement keeps the same integer results but re-expresses the state so that one
-// symbol costs a fixed, branch-light instruction sequence per thread:
+// symbol costs a fixed, branch-free instruction sequence per thread (the kernel is integer-issue bound):
 //
-//   state     reference keeps (start_range, end_range) (bac.c:83); we keep (lo, rng) with rng = hi - lo + 1,
-//             because every renormalisation step doubles rng whatever branch it takes.
+//   state     reference keeps (start_range, end_range) (bac.c:83); we keep (LO, rng): LO = start_range << 16
+//             (top-aligned in a 32-bit register) and rng = end - start + 1, because every renormalisation step
+//             doubles rng whatever branch it takes.
 //   model     the reference keeps freq[4]/cum[4]/two index maps (bac.c:33-37).  EOF never moves and keeps
-//             frequency 1 (UpdateModel is never called with index 3; halving maps 1 -> 1, bac.c:63), and index 0
-//             is a sentinel, so the whole adaptive model is (f_top, f_oth, top): the counts of the data symbol at
-//             index 1 / index 2 and which bit sits at index 1.  cum[] = {f_top + f_oth + 1, f_oth + 1, 1, 0}.
-//   update    index 1: hi unchanged, lo += A                    A = floor(rng * (f_oth + 1) / total)
+//             frequency 1 (UpdateModel is never called with index 3; halving maps 1 -> 1, bac.c:63) and index 0 is
+//             a sentinel, so the whole adaptive model is (f_top, c1 = f_oth + 1, topmask, total): the counts of
+//             the data symbols at index 1 / 2 and which bit sits at index 1.  cum[] = {total, c1, 1, 0}.
+//   update    index 1: hi unchanged, lo += A                    A = floor(rng * c1 / total)
 //             index 2: lo += B, rng = A - B                      B = floor(rng / total)
 //             EOF    : rng = B                                    (bac.c:109-111 with the cum[] above)
-//   division  total <= 16383 and rng * cum < 2^30, so floor(x / total) == umulhi(x << 2, m) >> l with a
+//   division  total <= 16383 and rng * c1 <= 2^29, so floor(x / total) == umulhi(x << 2, m) >> l with a
 //             precomputed round-up reciprocal (m, l) per divisor (kernels.h: DivEntry); exact, no correction step.
 //   renorm    bac.c:112-137 is a loop of three cases.  Closed form: first n1 = number of equal leading bits of
 //             (lo, hi) "E1/E2" steps, each emitting that bit; then n3 = length of the run "lo = 01..., hi = 10..."
 //             below the top bit, each an "E3" step (pending++).  After an E3 step lo < 0x8000 <= hi, so no E1/E2
-//             step can follow within the same symbol.  Both counts come from one CLZ each.
+//             step can follow within the same symbol.  With HI = (hi << 16) | 0xFFFF both counts are one CLZ each
+//             and the low ones of HI cap them without a special case for lo == hi.
+//   emission  OutputNextBits (bac.c:93-105) writes a bit followed by `pending` inverted bits.  For n1 >= 1 E1/E2
+//             steps the output is the top n1 bits of lo with the pending run spliced in after the first one, i.e.
+//             the (n1 + pending)-bit number  bits + 2^(n1+pending-1) - 2^(n1-1)  -- one append, no loop.
 #pragma once
 
 #include <stdint.h>
@@ -29,94 +34,111 @@
 namespace dc {
 
 static const uint32_t kBacMaxFreq = 0x3FFFu;   // MAX_FREQUENCY, bac.c:27
+static const uint32_t kBacMaxFastPending = 16; // longer pending runs take the generic emitter
 
-struct BacModel
+// PTX shifts clamp the amount to 32 (C++ shifts by >= 32 are undefined)
+#ifdef DC_HOST_SIM
+static inline uint32_t shl_c(uint32_t a, uint32_t n) { return n >= 32 ? 0u : a << n; }
+static inline uint32_t shr_c(uint32_t a, uint32_t n) { return n >= 32 ? 0u : a >> n; }
+#else
+__device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n)
 {
-  uint32_t f_top;   // freq[1]
-  uint32_t f_oth;   // freq[2]
-  uint32_t top;     // index_to_symbol[1]
-  uint32_t total;   // cum[0]
-
-  __device__ __forceinline__ void init()   // InitModel, bac.c:39-52
-  {
-    f_top = 1;
-    f_oth = 1;
-    top = 0;
-    total = 3;
-  }
-
-  // UpdateModel, bac.c:54-81, for a data symbol (bit b; is_top == (b == top) evaluated before the update)
-  __device__ __forceinline__ void update(uint32_t b, bool is_top)
-  {
-    if (total == kBacMaxFreq)   // bac.c:57-67: halve, rounding up; EOF stays at 1
-    {
-      f_top = (f_top + 1) >> 1;
-      f_oth = (f_oth + 1) >> 1;
-      total = f_top + f_oth + 1;
-    }
-    if (is_top)
-      f_top++;
-    else if (f_oth == f_top)    // bac.c:68-77: the coded symbol moves left past its equal-frequency neighbour
-    {
-      top = b;
-      f_top++;
-    }
-    else
-      f_oth++;
-    total++;
-  }
-};
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint32_t shr_c(uint32_t a, uint32_t n)
+{
+  uint32_t r;
+  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));
+  return r;
+}
+#endif
 
 // floor(x / d) for x < 2^30 with the table entry of d
 __device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x << 2, e.m) >> e.l; }
 
-// Number of E1/E2 and E3 steps for the interval (lo, rng), and the renormalised interval (bac.c:112-137).
-__device__ __forceinline__ void bac_renorm(uint32_t &lo, uint32_t &rng, uint32_t &n1, uint32_t &n3)
+struct BacModel
 {
-  const uint32_t hi = lo + rng - 1;
-  n1 = __clz(lo ^ hi) - 16;              // equal leading bits of two 16-bit values (16 when lo == hi)
-  const uint32_t lo1 = (lo << n1) & 0xFFFFu;
-  const uint32_t rng1 = rng << n1;
-  const uint32_t hi1 = lo1 + rng1 - 1;
-  const uint32_t y = (~lo1 | hi1) & 0x7FFFu;   // bit clear where lo has 1 and hi has 0
-  n3 = __clz((y << 17) | 0x10000u);
-  lo = (lo1 << n3) & 0x7FFFu;
-  rng = rng1 << n3;
+  uint32_t f_top;     // freq[1]
+  uint32_t c1;        // cum[1] = freq[2] + 1
+  uint32_t topmask;   // index_to_symbol[1] as 0 / 0x80000000
+  uint32_t total;     // cum[0]
+
+  __device__ __forceinline__ void init()   // InitModel, bac.c:39-52
+  {
+    f_top = 1;
+    c1 = 2;
+    topmask = 0;
+    total = 3;
+  }
+
+  // bac.c:57-67: halve, rounding up; EOF stays at 1.  Only when total == kBacMaxFreq.
+  __device__ __forceinline__ void halve()
+  {
+    f_top = (f_top + 1) >> 1;
+    c1 = (c1 >> 1) + 1;          // ((c1 - 1) + 1) / 2 + 1
+    total = f_top + c1;
+  }
+
+  // UpdateModel, bac.c:68-80, for a data symbol; bm = the coded bit as 0 / 0x80000000, is_top == (bm == topmask)
+  __device__ __forceinline__ void bump(uint32_t bm, bool is_top)
+  {
+    const bool tie = (c1 - 1 == f_top);   // bac.c:68: the coded symbol moves left past its equal-frequency neighbour
+    const bool inc_top = is_top || tie;
+    const uint32_t inc = inc_top ? 1u : 0u;
+    topmask = inc_top ? bm : topmask;     // is_top: bm == topmask already; tie: the coded symbol takes index 1
+    f_top += inc;
+    c1 += 1u - inc;
+    total++;
+  }
+};
+
+// Interval after coding a symbol: LO0 (top-aligned lo), r1 (range).  Returns the E1/E2 count n1 and E3 count n3 and
+// leaves the renormalised interval in (LO, rng).  bac.c:112-137.
+__device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3)
+{
+  const uint32_t HI = LO0 + (r1 << 16) - 1;   // (hi << 16) | 0xFFFF
+  n1 = __clz(LO0 ^ HI);                       // 0..16
+  const uint32_t z = ~LO0 | HI;               // clear exactly where lo has 1 and hi has 0
+  n3 = __clz((z << n1) << 1);                 // run below the first differing bit, capped by the guard ones
+  const uint32_t n = n1 + n3;
+  rng = r1 << n;
+  LO = (LO0 << n) & 0x7FFF0000u;
 }
 
 struct BacEncoder
 {
-  uint32_t lo;      // start_range
+  uint32_t LO;      // start_range << 16
   uint32_t rng;     // end_range - start_range + 1, in [1, 65536]
-  uint64_t pend;    // next_bits, bac.c:84
+  uint32_t pend;    // next_bits, bac.c:84
 
   __device__ __forceinline__ void init()   // StartEncoding, bac.c:86-91
   {
-    lo = 0;
+    LO = 0;
     rng = 0x10000u;
     pend = 0;
   }
 
-  // renormalise and emit (bac.c:112-137 + OutputNextBits, bac.c:93-105)
-  __device__ __forceinline__ void renorm_emit(BitWriter &w)
+  // renormalise (LO0, r1) and emit (bac.c:112-137 + OutputNextBits, bac.c:93-105)
+  __device__ __forceinline__ void renorm_emit(uint32_t LO0, uint32_t r1, BitWriter &w)
   {
-    const uint32_t lo0 = lo;
     uint32_t n1, n3;
-    bac_renorm(lo, rng, n1, n3);
-    if (n1)
+    bac_renorm(LO0, r1, LO, rng, n1, n3);
+    const bool some = n1 != 0;
+    if (some && pend > kBacMaxFastPending)   // practically never: more than 16 consecutive E3 steps
     {
-      if (pend == 0)
-        w.put(lo0 >> (16 - n1), n1);
-      else
-      {
-        const uint32_t first = lo0 >> 15;
-        w.put(first, 1);
-        w.run(first ^ 1u, pend);
-        w.put((lo0 >> (16 - n1)) & ((1u << (n1 - 1)) - 1u), n1 - 1);
-        pend = 0;
-      }
+      const uint32_t first = LO0 >> 31;
+      w.put(first, 1);
+      w.run(first ^ 1u, pend);
+      w.put(shr_c(LO0 << 1, 33 - n1), n1 - 1);
+      pend = n3;
+      return;
     }
-    pend += n3;
+    const uint32_t bits = shr_c(LO0, 32 - n1);
+    const uint32_t k = some ? n1 + pend : 0u;
+    pend = (some ? 0u : pend) + n3;
+    w.put(bits + shl_c(1u, k - 1) - shl_c(1u, n1 - 1), k);
   }
 
   // EncodeSymbol for a data bit (bac.c:107-111)
@@ -124,28 +146,18 @@ struct BacEncoder
   {
     const uint32_t A = div_magic(rng * c1, e);
     const uint32_t B = div_magic(rng, e);
-    if (is_top)
-    {
-      lo += A;
-      rng -= A;
-    }
-    else
-    {
-      lo += B;
-      rng = A - B;
-    }
-    renorm_emit(w);
+    const uint32_t dlo = is_top ? A : B;
+    const uint32_t base = is_top ? rng : A;
+    renorm_emit(LO + (dlo << 16), base - dlo, w);
   }
 
   // EOF symbol (bac.c:163) followed by FinishEncoding (bac.c:141-145)
   __device__ __forceinline__ void finish(const DivEntry e, BitWriter &w)
   {
-    rng = div_magic(rng, e);
-    renorm_emit(w);
-    pend++;
-    const uint32_t bit = lo < 0x4000u ? 0u : 1u;
+    renorm_emit(LO, div_magic(rng, e), w);
+    const uint32_t bit = LO < 0x40000000u ? 0u : 1u;
     w.put(bit, 1);
-    w.run(bit ^ 1u, pend);
+    w.run(bit ^ 1u, (uint64_t)pend + 1);
     pend = 0;
   }
 };

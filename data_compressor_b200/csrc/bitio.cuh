@@ -40,7 +40,7 @@ struct BitWriter
   uint32_t nwords;
   uint32_t nacc;     // pending bits in acc, always < 32 between calls
   uint64_t acc;      // low nacc bits are pending
-  bool overflow;
+  bool overflow;     // valid after finish(): the stream outgrew cap_words (nothing is ever written past the end)
 
   __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes)
   {
@@ -58,8 +58,6 @@ struct BitWriter
     const uint32_t w = (uint32_t)(acc >> nacc);
     if (nwords < cap_words)
       words[nwords] = bswap32(w);
-    else
-      overflow = true;
     nwords++;
   }
 
@@ -113,14 +111,9 @@ struct BitWriter
   __device__ __forceinline__ uint64_t finish()
   {
     const uint64_t total = bits();
-    if (nacc)
-    {
-      const uint32_t w = (uint32_t)(acc << (32 - nacc));
-      if (nwords < cap_words)
-        words[nwords] = bswap32(w);
-      else
-        overflow = true;
-    }
+    overflow = nwords + (nacc ? 1u : 0u) > cap_words;
+    if (nacc && nwords < cap_words)
+      words[nwords] = bswap32((uint32_t)(acc << (32 - nacc)));
     return total;
   }
 };

@@ -84,3 +84,5 @@ static inline unsigned long long atomicExch(unsigned long long *p, unsigned long
   *p = v;
   return o;
 }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }

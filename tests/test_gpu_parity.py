@@ -74,6 +74,20 @@ def test_bac_random_bits(ctx, oracle, seed):
         assert ctx.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad) == oracle.run_chain([ob.BAC_DEC], got[1], got[2], adaptive=ad)
 
 
+def test_bac_long_pending_runs(ctx, oracle):
+    """Runs of middle-third symbols pile up E3 steps (pending > 16 leaves the branch-free emitter)."""
+    for n_ones in (5, 12, 20, 40, 1000):
+        for tail in ([], [0], [0, 1, 1, 0]):
+            bits = np.array([1] * n_ones + tail, dtype=np.uint8)
+            packed = np.packbits(bits)
+            for ad in (0, 1):
+                want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=ad)
+                got = ctx.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=ad)
+                assert got == want, (n_ones, tail, ad)
+                back = ctx.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad)
+                assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
+
+
 def test_garbage_and_truncated_inputs(ctx, oracle):
     rng = np.random.default_rng(9)
     junk = rng.integers(0, 256, 300, dtype=np.uint8)

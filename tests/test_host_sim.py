@@ -86,6 +86,21 @@ def test_bac_long_runs_force_halvings_and_pending_bits(sim, oracle):
     assert sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=1)[1] == packed.tobytes()
 
 
+def test_bac_long_pending_runs(sim, oracle):
+    """Static model: a '1' always takes the middle third, so runs of ones pile up E3 steps (pending > 16 takes the
+    generic emitter in bac.cuh); then a '0' or the end of the stream resolves them."""
+    for n_ones in (5, 11, 12, 20, 40, 100, 1000):
+        for tail in ([], [0], [0, 1, 1, 0]):
+            bits = np.array([1] * n_ones + tail, dtype=np.uint8)
+            packed = np.packbits(bits)
+            for ad in (0, 1):
+                want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=ad)
+                got = sim.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=ad)
+                assert got == want, (n_ones, tail, ad)
+                back = sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad)
+                assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_garbage_decoders_vs_oracle(sim, oracle, seed):
     rng = np.random.default_rng(90 + seed)
