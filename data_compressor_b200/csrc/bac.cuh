@@ -34,7 +34,6 @@
 namespace dc {
 
 static const uint32_t kBacMaxFreq = 0x3FFFu;   // MAX_FREQUENCY, bac.c:27
-static const uint32_t kBacMaxFastPending = 16; // longer pending runs take the generic emitter
 
 // PTX shifts clamp the amount to 32 (C++ shifts by >= 32 are undefined)
 #ifdef DC_HOST_SIM
@@ -55,41 +54,52 @@ __device__ __forceinline__ uint32_t shr_c(uint32_t a, uint32_t n)
 }
 #endif
 
+// Count of leading zeros of a NON-ZERO word: bfind.shiftamt is a single FLO.U32.SH (the generic __clz costs FLO + IADD)
+#ifdef DC_HOST_SIM
+static inline uint32_t clz_nz(uint32_t a) { return (uint32_t)__builtin_clz(a); }
+#else
+__device__ __forceinline__ uint32_t clz_nz(uint32_t a)
+{
+  uint32_t r;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
+#endif
+
 // floor(x / d) for x < 2^30 with the table entry of d
 __device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x << 2, e.m) >> e.l; }
 
 struct BacModel
 {
   uint32_t f_top;     // freq[1]
-  uint32_t c1;        // cum[1] = freq[2] + 1
   uint32_t topmask;   // index_to_symbol[1] as 0 / 0x80000000
-  uint32_t total;     // cum[0]
+  uint32_t total;     // cum[0] = freq[1] + freq[2] + 1, so cum[1] = freq[2] + 1 = total - f_top
 
   __device__ __forceinline__ void init()   // InitModel, bac.c:39-52
   {
     f_top = 1;
-    c1 = 2;
     topmask = 0;
     total = 3;
   }
 
+  __device__ __forceinline__ uint32_t c1() const { return total - f_top; }   // cum[1]
+
   // bac.c:57-67: halve, rounding up; EOF stays at 1.  Only when total == kBacMaxFreq.
   __device__ __forceinline__ void halve()
   {
+    const uint32_t f_oth = (total - f_top) >> 1;   // ((freq[2]) + 1) / 2 with freq[2] = total - f_top - 1
     f_top = (f_top + 1) >> 1;
-    c1 = (c1 >> 1) + 1;          // ((c1 - 1) + 1) / 2 + 1
-    total = f_top + c1;
+    total = f_top + f_oth + 1;
   }
 
   // UpdateModel, bac.c:68-80, for a data symbol; bm = the coded bit as 0 / 0x80000000, is_top == (bm == topmask)
   __device__ __forceinline__ void bump(uint32_t bm, bool is_top)
   {
-    const bool tie = (c1 - 1 == f_top);   // bac.c:68: the coded symbol moves left past its equal-frequency neighbour
-    const bool inc_top = is_top || tie;
-    const uint32_t inc = inc_top ? 1u : 0u;
+    // bac.c:68: a symbol at index 2 moves left past its equal-frequency neighbour (freq[2] == freq[1], i.e.
+    // total == 2 * freq[1] + 1), then freq[1]++; otherwise freq[2]++ (implied by total++)
+    const bool inc_top = is_top || (total == 2 * f_top + 1);
     topmask = inc_top ? bm : topmask;     // is_top: bm == topmask already; tie: the coded symbol takes index 1
-    f_top += inc;
-    c1 += 1u - inc;
+    f_top += inc_top ? 1u : 0u;
     total++;
   }
 };
@@ -99,9 +109,9 @@ struct BacModel
 __device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3)
 {
   const uint32_t HI = LO0 + (r1 << 16) - 1;   // (hi << 16) | 0xFFFF
-  n1 = __clz(LO0 ^ HI);                       // 0..16
+  n1 = clz_nz(LO0 ^ HI);                      // 0..16 (the low 16 bits of the xor are ones)
   const uint32_t z = ~LO0 | HI;               // clear exactly where lo has 1 and hi has 0
-  n3 = __clz((z << n1) << 1);                 // run below the first differing bit, capped by the guard ones
+  n3 = clz_nz((z << n1) << 1);                // run below the first differing bit, capped by the guard ones
   const uint32_t n = n1 + n3;
   rng = r1 << n;
   LO = (LO0 << n) & 0x7FFF0000u;
@@ -126,19 +136,25 @@ struct BacEncoder
     uint32_t n1, n3;
     bac_renorm(LO0, r1, LO, rng, n1, n3);
     const bool some = n1 != 0;
-    if (some && pend > kBacMaxFastPending)   // practically never: more than 16 consecutive E3 steps
+    const uint32_t k = some ? n1 + pend : 0u;   // bits leaving now: n1 plus the pending run spliced after the first
+    const uint32_t p0 = pend;
+    pend = (some ? 0u : pend) + n3;
+    // One rare region per symbol: the accumulator would reach a full word, or k > 32.
+    if (w.nacc + k >= 32)
     {
-      const uint32_t first = LO0 >> 31;
-      w.put(first, 1);
-      w.run(first ^ 1u, pend);
-      w.put(shr_c(LO0 << 1, 33 - n1), n1 - 1);
-      pend = n3;
+      if (k > 32)   // practically never: more than 16 consecutive E3 steps before this E1/E2 step
+      {
+        const uint32_t first = LO0 >> 31;
+        w.put(first, 1);
+        w.run(first ^ 1u, p0);
+        w.put(shr_c(LO0 << 1, 33 - n1), n1 - 1);
+      }
+      else
+        w.put(shr_c(LO0, 32 - n1) + shl_c(1u, k - 1) - shl_c(1u, n1 - 1), k);
       return;
     }
-    const uint32_t bits = shr_c(LO0, 32 - n1);
-    const uint32_t k = some ? n1 + pend : 0u;
-    pend = (some ? 0u : pend) + n3;
-    w.put(bits + shl_c(1u, k - 1) - shl_c(1u, n1 - 1), k);
+    w.acc = (w.acc << k) | (shr_c(LO0, 32 - n1) + shl_c(1u, k - 1) - shl_c(1u, n1 - 1));
+    w.nacc += k;
   }
 
   // EncodeSymbol for a data bit (bac.c:107-111)
