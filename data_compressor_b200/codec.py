@@ -166,6 +166,43 @@ class Context:
     def axdr_decode(self, enc: Encoded, vs: int = 32, nf: float = 100.0, out: torch.Tensor | None = None):
         return self._decode(self.lib.dc_axdr_decode_device, "dc_axdr_decode_device", enc, vs, nf, False, out)
 
+    # ---- LZMH: independent byte blocks ------------------------------------------------------------
+    def lzmh_encode(self, data: torch.Tensor, block_bytes: int = 65536, payload_cap: int | None = None):
+        """`encode lzmh` for every block of `block_bytes` bytes of a uint8 tensor (last block may be short).
+        Returns (payload, bit_len, byte_off, status, total_bytes, in_off)."""
+        assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
+        dev = data.device
+        nbytes = data.numel()
+        n = (nbytes + block_bytes - 1) // block_bytes if nbytes else 0
+        in_off = torch.clamp(torch.arange(n + 1, dtype=torch.int64, device=dev) * block_bytes, max=nbytes)
+        if payload_cap is None:
+            payload_cap = nbytes * 10 // 8 + n * 16 + 64
+        payload = torch.empty(int(payload_cap) + 16, dtype=torch.uint8, device=dev)
+        bit_len = torch.empty(n, dtype=torch.int64, device=dev)
+        byte_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        total = C.c_uint64(0)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = self.lib.dc_lzmh_encode_device(self.h, data.data_ptr(), in_off.data_ptr(), n, payload.data_ptr(), int(payload_cap),
+                                            bit_len.data_ptr(), byte_off.data_ptr(), status.data_ptr(), C.byref(total))
+        self._check(rc, "dc_lzmh_encode_device")
+        return payload, bit_len, byte_off, status, int(total.value), in_off
+
+    def lzmh_decode(self, payload: torch.Tensor, total_bytes: int, bit_len: torch.Tensor, byte_off: torch.Tensor,
+                    out_off: torch.Tensor):
+        """`decode lzmh` for every block; out_off[n+1] gives each block's output window."""
+        dev = payload.device
+        n = int(bit_len.numel())
+        out = torch.empty(int(out_off[-1].item()) if n else 0, dtype=torch.uint8, device=dev)
+        out_len = torch.empty(n, dtype=torch.int64, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = self.lib.dc_lzmh_decode_device(self.h, payload.data_ptr(), int(total_bytes), bit_len.data_ptr(), byte_off.data_ptr(), n,
+                                            out.data_ptr(), out_off.data_ptr(), out_len.data_ptr(), status.data_ptr())
+        self._check(rc, "dc_lzmh_decode_device")
+        self.synchronize()
+        return out, out_len, status
+
     # ---- host-buffer face (numpy in / numpy out; copies inside) -----------------------------------
     def dega_encode_host(self, samples: np.ndarray, block_len: int = 0, vs: int = 32, nf: float = 100.0,
                          adaptive: bool = True, payload_cap: int | None = None):

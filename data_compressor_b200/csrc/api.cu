@@ -707,6 +707,166 @@ int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_byte
   return DC_OK;
 }
 
+// ---- LZMH ---------------------------------------------------------------------------------------------------
+static uint64_t lzmh_enc_cap_bytes(uint64_t max_len) { return round_up((max_len * 10 + 7) / 8 + 16, 16); }   // worst case: every byte a 10-bit literal
+
+int dc_lzmh_encode_device(dc_ctx *c, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t n, uint8_t *d_payload, uint64_t payload_cap,
+                          uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status, uint64_t *total_bytes)
+{
+  if (!c || !d_in_off || !d_bit_len || !d_byte_off || !d_status)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  c->ev_mask = 0;
+  // block sizes are needed on the host to size the scratch stride
+  std::vector<uint64_t> off(n + 1);
+  CU_TRY(c, cudaMemcpyAsync(off.data(), d_in_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  uint64_t max_len = 0;
+  for (uint64_t s = 0; s < n; s++)
+  {
+    if (off[s + 1] < off[s])
+      return DC_ERR_INVALID_VALUE;
+    max_len = std::max(max_len, off[s + 1] - off[s]);
+  }
+  const uint64_t cap = lzmh_enc_cap_bytes(max_len);
+  const uint64_t n_tiles = (n + 4095) / 4096;
+  int rc = arena_reserve(c, Bump::size_of(n_tiles + 2, 8) + Bump::size_of(n * cap, 1) + 4096);
+  if (rc != DC_OK)
+    return rc;
+  Bump b(c->arena);
+  uint64_t *d_tiles = b.take<uint64_t>(n_tiles + 2);
+  uint8_t *d_scratch = b.take<uint8_t>(n * cap);
+  LzmhArgs la;
+  memset(&la, 0, sizeof(la));
+  la.n_streams = n;
+  la.in = d_in;
+  la.in_off = d_in_off;
+  la.bits_out.base = d_scratch;
+  la.bits_out.stride_bytes = cap;
+  la.bits_out.nbits = d_bit_len;
+  la.status = d_status;
+  {
+    Timed t(c, DC_K_LZMH_ENC);
+    launch_lzmh_encode(la, c->stream);
+  }
+  {
+    Timed t(c, DC_K_SCAN);
+    launch_byte_scan(d_bit_len, n, d_byte_off, d_tiles, c->stream);
+  }
+  {
+    Timed t(c, DC_K_GATHER);
+    launch_gather(d_scratch, cap, d_bit_len, d_byte_off, n, d_payload, payload_cap, c->stream);
+  }
+  if ((rc = check_launch(c, "lzmh encode kernels")) != DC_OK)
+    return rc;
+  uint64_t tot = 0;
+  if ((rc = read_back(c, d_byte_off + n, &tot, 1)) != DC_OK)
+    return rc;
+  if (total_bytes)
+    *total_bytes = tot;
+  if (tot > payload_cap)
+  {
+    set_err(c, "payload needs %llu bytes, capacity is %llu", (unsigned long long)tot, (unsigned long long)payload_cap);
+    return DC_ERR_MEMORY;
+  }
+  return DC_OK;
+}
+
+int dc_lzmh_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes, const uint64_t *d_bit_len,
+                          const uint64_t *d_byte_off, uint64_t n, uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len,
+                          int32_t *d_status)
+{
+  (void)payload_bytes;
+  if (!c || !d_bit_len || !d_byte_off || !d_out_off || !d_out_len || !d_status)
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  c->ev_mask = 0;
+  LzmhArgs la;
+  memset(&la, 0, sizeof(la));
+  la.n_streams = n;
+  la.bits_in.base = d_payload;
+  la.bits_in.byte_off = d_byte_off;
+  la.bits_in.nbits = d_bit_len;
+  la.out = d_out;
+  la.out_off = d_out_off;
+  la.out_len = d_out_len;
+  la.status = d_status;
+  {
+    Timed t(c, DC_K_LZMH_DEC);
+    launch_lzmh_decode(la, c->stream);
+  }
+  return check_launch(c, "lzmh_decode_kernel");
+}
+
+// one LZMH stage over one host stream (plugin face)
+static int lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_bits)
+{
+  const uint64_t in_bytes = (in_bits + 7) / 8;
+  if (encode && (in_bits & 7))
+    return DC_ERR_LIBRARY_CALL;   // 8-bit reads (lzmh.c:165): a fractional last byte is a short read
+  for (unsigned boost = 1;; boost *= 8)
+  {
+    const uint64_t dev_cap = encode ? lzmh_enc_cap_bytes(in_bytes) : round_up((in_bytes * 8 + 4096) * boost, 16);
+    int rc = arena_reserve(c, Bump::size_of(in_bytes + 64, 1) + Bump::size_of(dev_cap + 64, 1) + Bump::size_of(16, 8) + 4096);
+    if (rc != DC_OK)
+      return rc;
+    Bump b(c->arena);
+    uint8_t *d_in = b.take<uint8_t>(in_bytes + 64);
+    uint8_t *d_out = b.take<uint8_t>(dev_cap + 64);
+    uint64_t *d_meta = b.take<uint64_t>(16);   // [0..1] in_off / out_off, [2] bits in, [3] bits/bytes out, [4] status
+    const uint64_t meta[6] = { 0, encode ? in_bytes : dev_cap, in_bits, 0, 0, 0 };
+    CU_TRY(c, cudaMemcpyAsync(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemsetAsync(d_in + (in_bytes & ~(uint64_t)15), 0, 32, c->stream), DC_ERR_LIBRARY_CALL);
+    if (in_bytes)
+      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    LzmhArgs la;
+    memset(&la, 0, sizeof(la));
+    la.n_streams = 1;
+    la.status = reinterpret_cast<int32_t *>(d_meta + 4);
+    if (encode)
+    {
+      la.in = d_in;
+      la.in_off = d_meta;
+      la.bits_out.base = d_out;
+      la.bits_out.stride_bytes = dev_cap;
+      la.bits_out.nbits = d_meta + 3;
+      launch_lzmh_encode(la, c->stream);
+    }
+    else
+    {
+      la.bits_in.base = d_in;
+      la.bits_in.byte_off = nullptr;
+      la.bits_in.stride_bytes = 0;
+      la.bits_in.nbits = d_meta + 2;
+      la.out = d_out;
+      la.out_off = d_meta;
+      la.out_len = d_meta + 3;
+      launch_lzmh_decode(la, c->stream);
+    }
+    if ((rc = check_launch(c, "lzmh stage kernel")) != DC_OK)
+      return rc;
+    uint64_t back[6];
+    if ((rc = read_back(c, d_meta, back, 6)) != DC_OK)
+      return rc;
+    const int32_t st = (int32_t)(back[4] & 0xFFFFFFFFu);
+    if (st == DC_ERR_MEMORY && !encode && boost < 4096)
+      continue;   // decoded stream outgrew the guess: retry with a larger window
+    if (st != 0)
+      return st;
+    const uint64_t bits = encode ? back[3] : back[3] * 8;
+    *out_bits = bits;
+    const uint64_t nbytes = (bits + 7) / 8;
+    if (nbytes > out_cap)
+      return DC_ERR_MEMORY;
+    if (nbytes)
+    {
+      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+    }
+    return DC_OK;
+  }
+}
+
 // ---- plugin face: one stage over one stream ---------------------------------------------------------------
 uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *p)
 {
@@ -729,8 +889,6 @@ uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *p)
   }
 }
 
-int dc_lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_bits);
-
 int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits, const dc_params *params, uint8_t *out, uint64_t out_cap,
                       uint64_t *out_bits)
 {
@@ -739,7 +897,7 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
   *out_bits = 0;
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
   if (stage == DC_STAGE_LZMH_ENC || stage == DC_STAGE_LZMH_DEC)
-    return dc_lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_bits, out, out_cap, out_bits);
+    return lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_bits, out, out_cap, out_bits);
 
   const uint32_t vs = params->value_size_bits;
   const uint64_t in_bytes = (in_bits + 7) / 8;

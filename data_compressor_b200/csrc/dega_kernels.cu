@@ -12,6 +12,7 @@ namespace dc {
 
 static uint64_t g_launches = 0;
 uint64_t launch_counter() { return g_launches; }
+void count_launch(int n) { g_launches += (uint64_t)n; }
 
 __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
 {

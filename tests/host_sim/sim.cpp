@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../data_compressor_b200/csrc/dega_device.cuh"
+#include "../../data_compressor_b200/csrc/lzmh_device.cuh"
 #include "../../include/dc_cuda.h"
 
 using namespace dc;
@@ -204,6 +205,26 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       memcpy(out, h_out.data(), nbytes);
     return DC_OK;
   }
+}
+
+// LZMH decode of one stream through the device body (the encoder is warp-cooperative and is tested on the GPU only)
+int sim_lzmh_decode(const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_len)
+{
+  std::vector<uint8_t> h_in((in_bits + 7) / 8 + 64, 0);
+  if (in_bits)
+    memcpy(h_in.data(), in, (in_bits + 7) / 8);
+  uint64_t nb = in_bits, off[2] = { 0, out_cap };
+  int32_t status = 0;
+  LzmhArgs la;
+  memset(&la, 0, sizeof(la));
+  la.n_streams = 1;
+  la.bits_in = BitSrc{ h_in.data(), nullptr, 0, &nb };
+  la.out = out;
+  la.out_off = off;
+  la.out_len = out_len;
+  la.status = &status;
+  lzmh_decode_body(la, 0);
+  return status;
 }
 
 // Batch DEGA encode over a uniform layout on host memory; writes per-stream payloads back to back (dense) the way
