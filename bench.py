@@ -27,7 +27,7 @@ if ROOT not in sys.path:
 
 CHANNELS = 4096
 SAMPLES = 86400
-BLOCK_LEN = 1024
+BLOCK_LEN = 1168   # 74 blocks per channel-day -> 303104 streams = exactly 2 waves of 148 SMs x 1024 threads
 VS, NF, ADAPTIVE = 32, 100.0, True
 METRIC = "DEGA encode+decode GB/s of raw samples"
 
@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -208,13 +208,12 @@ def run_ours(args):
 
     enc = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)       # allocates outputs + arena once
     y = torch.empty_like(x)
-    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    from data_compressor_b200 import shard
 
     def step():
         e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
-        if world > 1:   # the only collective on the path: per-shard payload byte counts -> container offsets
-            mine = torch.tensor([e.total_bytes], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(sizes, mine)
+        # the only collective on the path: per-shard payload byte counts -> container offsets (8 B per rank)
+        shard.exchange_sizes(e.total_bytes, e.n_streams, dev)
         ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
         return e
 
@@ -242,8 +241,7 @@ def run_ours(args):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
             if world > 1:
-                mine = torch.tensor([e.total_bytes], dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(sizes, mine)
+                shard.exchange_sizes(e.total_bytes, e.n_streams, dev)
             ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
             km2 = ctx.kernel_ms()
             for k, v in list(km.items()) + list(km2.items()):

@@ -204,18 +204,29 @@ class Context:
         return out, out_len, status
 
     # ---- host-buffer face (numpy in / numpy out; copies inside) -----------------------------------
+    def _pinned(self, key: str, nbytes: int) -> np.ndarray:
+        """Reusable page-locked host buffer (uint8 view); the *_host calls copy with cudaMemcpyAsync."""
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        buf = cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, pin_memory=True)
+            cache[key] = buf
+        return buf.numpy()[:nbytes]
+
     def dega_encode_host(self, samples: np.ndarray, block_len: int = 0, vs: int = 32, nf: float = 100.0,
                          adaptive: bool = True, payload_cap: int | None = None):
+        """Host-buffer face (dc_dega_encode_host).  Outputs live in reusable pinned buffers owned by the context:
+        they stay valid until the next *_host encode call."""
         x = np.ascontiguousarray(samples, dtype=np.float32)
         assert x.ndim == 2
         n_channels, channel_len = x.shape
         n = self.n_streams(n_channels, channel_len, block_len)
         if payload_cap is None:
             payload_cap = x.size * 4 + n * 16 + 64
-        payload = np.empty(payload_cap, dtype=np.uint8)
-        bit_len = np.empty(n, dtype=np.uint64)
-        byte_off = np.empty(n + 1, dtype=np.uint64)
-        status = np.empty(n, dtype=np.int32)
+        payload = self._pinned("enc_payload", payload_cap)
+        bit_len = self._pinned("enc_bit_len", n * 8).view(np.uint64)
+        byte_off = self._pinned("enc_byte_off", (n + 1) * 8).view(np.uint64)
+        status = self._pinned("enc_status", n * 4).view(np.int32)
         total = C.c_uint64(0)
         lay = self._layout(n_channels, channel_len, block_len)
         par = self._params(vs, nf, adaptive)
@@ -231,9 +242,9 @@ class Context:
         bl = np.ascontiguousarray(bit_len, dtype=np.uint64)
         bo = np.ascontiguousarray(byte_off, dtype=np.uint64)
         n = bl.size
-        out = np.empty((n_channels, channel_len), dtype=np.float32)
-        n_out = np.empty(n, dtype=np.uint64)
-        status = np.empty(n, dtype=np.int32)
+        out = self._pinned("dec_samples", n_channels * channel_len * 4).view(np.float32).reshape(n_channels, channel_len)
+        n_out = self._pinned("dec_n_out", n * 8).view(np.uint64)
+        status = self._pinned("dec_status", n * 4).view(np.int32)
         lay = self._layout(n_channels, channel_len, block_len)
         par = self._params(vs, nf, adaptive)
         rc = self.lib.dc_dega_decode_host(self.h, p.ctypes.data, p.size, bl.ctypes.data, bo.ctypes.data, C.byref(lay),

@@ -21,9 +21,10 @@ struct dc_ctx
   int device;
   cudaStream_t stream;
   DivEntry *d_div;
-  uint8_t *arena;
+  uint8_t *arena;        // kernel scratch (SEG / coder strides), grown on demand
   uint64_t arena_size;
-  uint64_t arena_used;
+  uint8_t *stage;        // device staging of the host-buffer calls (samples, payload, index), grown on demand
+  uint64_t stage_size;
   uint64_t *h_pinned;   // small pinned mailbox for device->host scalars
   uint64_t launches_base;
   int profiling;
@@ -99,6 +100,27 @@ int arena_reserve(dc_ctx *c, uint64_t bytes)
     return DC_OK;
   }
   c->arena_size = want;
+  return DC_OK;
+}
+
+// same policy for the staging block of the *_host calls
+int stage_reserve(dc_ctx *c, uint64_t bytes)
+{
+  if (bytes <= c->stage_size)
+    return DC_OK;
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  if (c->stage)
+    cudaFree(c->stage);
+  c->stage = nullptr;
+  c->stage_size = 0;
+  const uint64_t want = round_up(bytes, 1 << 20);
+  if (cudaMalloc(&c->stage, want) != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_err(c, "device staging allocation of %llu bytes failed", (unsigned long long)bytes);
+    return DC_ERR_MEMORY;
+  }
+  c->stage_size = want;
   return DC_OK;
 }
 
@@ -393,34 +415,6 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
   return check_launch(c, "back_kernel");
 }
 
-// Device staging buffers for the host-facing calls are plain cudaMalloc allocations owned by the call.
-struct DevBuf
-{
-  void *p = nullptr;
-  ~DevBuf()
-  {
-    if (p)
-      cudaFree(p);
-  }
-  int alloc(dc_ctx *c, uint64_t bytes)
-  {
-    if (cudaMalloc(&p, std::max<uint64_t>(bytes, 16)) != cudaSuccess)
-    {
-      cudaGetLastError();
-      set_err(c, "device allocation of %llu bytes failed", (unsigned long long)bytes);
-      p = nullptr;
-      return DC_ERR_MEMORY;
-    }
-    return DC_OK;
-  }
-  template <typename T>
-  T *as()
-  {
-    return static_cast<T *>(p);
-  }
-};
-
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -481,6 +475,8 @@ void dc_destroy(dc_ctx *c)
     cudaStreamSynchronize(c->stream);
   if (c->arena)
     cudaFree(c->arena);
+  if (c->stage)
+    cudaFree(c->stage);
   if (c->d_div)
     cudaFree(c->d_div);
   if (c->h_pinned)
@@ -630,33 +626,38 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
   if (rc != DC_OK)
     return rc;
   const uint64_t n = L.n_streams;
-  DevBuf d_samples, d_off, d_payload, d_bits, d_boff, d_status;
-  if ((rc = d_samples.alloc(c, total * 4)) || (rc = d_payload.alloc(c, round_up(payload_cap, 4) + 16)) || (rc = d_bits.alloc(c, n * 8)) ||
-      (rc = d_boff.alloc(c, (n + 1) * 8)) || (rc = d_status.alloc(c, n * 4)))
+  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_cap, 4) + 16, 1) + Bump::size_of(n, 8) +
+                        2 * Bump::size_of(n + 1, 8) + Bump::size_of(n, 4) + 4096;
+  if ((rc = stage_reserve(c, need)) != DC_OK)
     return rc;
+  Bump b(c->stage);
+  float *d_samples = b.take<float>(total);
+  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_cap, 4) + 16);
+  uint64_t *d_bits = b.take<uint64_t>(n);
+  uint64_t *d_boff = b.take<uint64_t>(n + 1);
+  uint64_t *d_off = b.take<uint64_t>(n + 1);
+  int32_t *d_status = b.take<int32_t>(n);
   if (layout->sample_off)
   {
-    if ((rc = d_off.alloc(c, (n + 1) * 8)))
-      return rc;
-    CU_TRY(c, cudaMemcpyAsync(d_off.p, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-    L.sample_off = d_off.as<uint64_t>();
+    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    L.sample_off = d_off;
   }
-  CU_TRY(c, cudaMemcpyAsync(d_samples.p, samples, total * 4, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  if (total)
+    CU_TRY(c, cudaMemcpyAsync(d_samples, samples, total * 4, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
   uint64_t tot = 0;
-  rc = encode_pipeline(c, FRONT_DEGA, d_samples.as<float>(), L, max_len, params, d_payload.as<uint8_t>(), payload_cap,
-                       d_bits.as<uint64_t>(), d_boff.as<uint64_t>(), d_status.as<int32_t>(), &tot);
+  rc = encode_pipeline(c, FRONT_DEGA, d_samples, L, max_len, params, d_payload, payload_cap, d_bits, d_boff, d_status, &tot);
   if (total_bytes)
     *total_bytes = tot;
   if (rc != DC_OK && rc != DC_ERR_MEMORY)
     return rc;
-  if (bit_len)
-    CU_TRY(c, cudaMemcpyAsync(bit_len, d_bits.p, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (bit_len && n)
+    CU_TRY(c, cudaMemcpyAsync(bit_len, d_bits, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
   if (byte_off)
-    CU_TRY(c, cudaMemcpyAsync(byte_off, d_boff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (status)
-    CU_TRY(c, cudaMemcpyAsync(status, d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(byte_off, d_boff, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (status && n)
+    CU_TRY(c, cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
   if (rc == DC_OK && payload && tot)
-    CU_TRY(c, cudaMemcpyAsync(payload, d_payload.p, tot, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(payload, d_payload, tot, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
   CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
   return rc;
 }
@@ -673,30 +674,37 @@ int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_byte
   if (rc != DC_OK)
     return rc;
   const uint64_t n = L.n_streams;
-  DevBuf d_samples, d_off, d_payload, d_bits, d_boff, d_status, d_nout;
-  if ((rc = d_samples.alloc(c, total * 4)) || (rc = d_payload.alloc(c, round_up(payload_bytes, 4) + 16)) || (rc = d_bits.alloc(c, n * 8)) ||
-      (rc = d_boff.alloc(c, (n + 1) * 8)) || (rc = d_status.alloc(c, n * 4)) || (rc = d_nout.alloc(c, n * 8)))
+  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_bytes, 4) + 16, 1) + 2 * Bump::size_of(n, 8) +
+                        2 * Bump::size_of(n + 1, 8) + Bump::size_of(n, 4) + 4096;
+  if ((rc = stage_reserve(c, need)) != DC_OK)
     return rc;
+  Bump b(c->stage);
+  float *d_samples = b.take<float>(total);
+  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_bytes, 4) + 16);
+  uint64_t *d_bits = b.take<uint64_t>(n);
+  uint64_t *d_nout = b.take<uint64_t>(n);
+  uint64_t *d_boff = b.take<uint64_t>(n + 1);
+  uint64_t *d_off = b.take<uint64_t>(n + 1);
+  int32_t *d_status = b.take<int32_t>(n);
   if (layout->sample_off)
   {
-    if ((rc = d_off.alloc(c, (n + 1) * 8)))
-      return rc;
-    CU_TRY(c, cudaMemcpyAsync(d_off.p, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-    L.sample_off = d_off.as<uint64_t>();
+    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    L.sample_off = d_off;
   }
-  CU_TRY(c, cudaMemcpyAsync(d_payload.p, payload, payload_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaMemcpyAsync(d_bits.p, bit_len, n * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaMemcpyAsync(d_boff.p, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  rc = decode_pipeline(c, FRONT_DEGA, d_payload.as<uint8_t>(), d_bits.as<uint64_t>(), d_boff.as<uint64_t>(), L, max_len, params,
-                       d_samples.as<float>(), d_nout.as<uint64_t>(), d_status.as<int32_t>());
+  if (payload_bytes)
+    CU_TRY(c, cudaMemcpyAsync(d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  if (n)
+    CU_TRY(c, cudaMemcpyAsync(d_bits, bit_len, n * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemcpyAsync(d_boff, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  rc = decode_pipeline(c, FRONT_DEGA, d_payload, d_bits, d_boff, L, max_len, params, d_samples, d_nout, d_status);
   if (rc != DC_OK)
     return rc;
   if (samples && total)
-    CU_TRY(c, cudaMemcpyAsync(samples, d_samples.p, total * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (n_out)
-    CU_TRY(c, cudaMemcpyAsync(n_out, d_nout.p, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (status)
-    CU_TRY(c, cudaMemcpyAsync(status, d_status.p, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(samples, d_samples, total * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (n_out && n)
+    CU_TRY(c, cudaMemcpyAsync(n_out, d_nout, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  if (status && n)
+    CU_TRY(c, cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
   CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)

@@ -1,0 +1,172 @@
+/* dc_cuda_plugin.c -- DCLib-side glue: enc_dec_function_t bodies that run on the GPU.
+ *
+ * This is the file a Data Compressor maintainer adds to DCLib.  It is C90 like the rest of
+ * the reference, includes only the reference's public headers (DCLib/inc/enc_dec.h, io_macros.h) and the C ABI of
+ * libdc_cuda.so (include/dc_cuda.h).  Every function has the plugin signature of DCLib/inc/enc_dec.h:11:
+ *
+ *   io_int_t f(bit_file_buffer_t *in, bit_file_buffer_t *out, const options_t *options)
+ *
+ * and follows the contract of SURVEY.md section 8b: read until EndOfBitFileBuffer(in), write the exact number of
+ * result bits, never flush/close the buffers, return NO_ERROR or a negative code of common/inc/err_codes.h.
+ *
+ * Two ways to register them:
+ *   (a) new names next to the CPU codecs: "dega", "gpu_bac", ... (two-line edit of the table in enc_dec.c), or
+ *   (b) -DDC_CUDA_REPLACE_REFERENCE: this file then defines Normalize, EncodeDifferential, EncodeSEG, EncodeBAC,
+ *       EncodeLZMH and their decoders themselves, so linking it INSTEAD of normalize.c/diff.c/seg.c/bac.c/lzmh.c
+ *       gives a DCCLI whose unchanged command lines run on the GPU.  oracle/Makefile builds that binary as
+ *       oracle/_ref/DCCLI_cuda for the drop-in test.
+ */
+#include "err_codes.h"
+#include "io_macros.h"
+#include "enc_dec.h"
+
+#include "dc_cuda.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+static dc_ctx *g_ctx = NULL;
+
+static io_int_t GetContext(dc_ctx **ctx, FILE * const error_log_file)
+{
+  if (g_ctx == NULL)
+  {
+    const char * const dev = getenv("DC_CUDA_DEVICE");
+    const int ret = dc_create(&g_ctx, dev != NULL ? atoi(dev) : 0);
+    if (ret != DC_OK)
+    {
+      LOG_ERROR(error_log_file, "Could not create a CUDA context (no usable GPU?); there is no CPU fallback\n");
+      g_ctx = NULL;
+      return ERROR_LIBRARY_INIT;
+    }
+  }
+  *ctx = g_ctx;
+  return NO_ERROR;
+}
+
+/* Drains the whole input bit buffer; *bits receives the exact bit count (the in-chain hand-off keeps fractional
+   bytes, DCIOLib/src/bit_file_buffer.c:135-141,169-176). */
+static io_int_t DrainInput(bit_file_buffer_t * const in_bit_buf, uint8_t ** const data, io_uint_t * const bits)
+{
+  size_t capacity = 1 << 16, used = 0;
+  uint8_t *buffer = (uint8_t*)malloc(capacity);
+  *bits = 0;
+  *data = NULL;
+  if (buffer == NULL)
+    return ERROR_MEMORY;
+  while (!EndOfBitFileBuffer(in_bit_buf))
+  {
+    const size_t chunk = 1 << 15; /* bytes */
+    io_int_t got;
+    if (used + chunk > capacity)
+    {
+      uint8_t *bigger;
+      capacity *= 2;
+      if ((bigger = (uint8_t*)realloc(buffer, capacity)) == NULL)
+      {
+        free(buffer);
+        return ERROR_MEMORY;
+      }
+      buffer = bigger;
+    }
+    got = ReadBitFileBuffer(in_bit_buf, buffer + used, 8 * chunk);
+    if (got < 0)
+    {
+      free(buffer);
+      return got;
+    }
+    *bits += (io_uint_t)got;
+    used += (size_t)((got + 7) / 8);
+    if ((size_t)got != 8 * chunk) /* Short read: end of input (possibly inside a byte) */
+      break;
+  }
+  *data = buffer;
+  return NO_ERROR;
+}
+
+static io_int_t RunStage(const int stage, bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options)
+{
+  dc_ctx *ctx;
+  dc_params params;
+  uint8_t *in_data, *out_data;
+  io_uint_t in_bits;
+  uint64_t out_bits = 0, out_capacity;
+  io_int_t ret;
+  int attempt;
+  if ((ret = GetContext(&ctx, options->error_log_file)) != NO_ERROR)
+    return ret;
+  if ((ret = DrainInput(in_bit_buf, &in_data, &in_bits)) != NO_ERROR)
+    return ret;
+  params.value_size_bits = (uint32_t)options->value_size_bits;
+  params.normalization_factor = options->normalization_factor;
+  params.adaptive = options->adaptive;
+  params.reserved = 0;
+  out_capacity = dc_stage_out_bound(stage, in_bits, &params);
+  out_data = NULL;
+  for (attempt = 0; attempt < 2; attempt++)
+  {
+    if ((out_data = (uint8_t*)malloc((size_t)out_capacity + 16)) == NULL)
+    {
+      free(in_data);
+      return ERROR_MEMORY;
+    }
+    ret = dc_stage_run_host(ctx, stage, in_data, in_bits, &params, out_data, out_capacity, &out_bits);
+    if (ret != DC_ERR_MEMORY || out_bits == 0)
+      break;
+    free(out_data); /* The library reported the exact size it needs: retry once */
+    out_data = NULL;
+    out_capacity = (out_bits + 7) / 8 + 16;
+  }
+  free(in_data);
+  if (ret != NO_ERROR)
+  {
+    if (out_data != NULL)
+      free(out_data);
+    if (ret == ERROR_LIBRARY_CALL || ret == ERROR_LIBRARY_INIT)
+      LOG_ERROR(options->error_log_file, "CUDA stage %d failed: %s\n", stage, dc_last_error(ctx));
+    return ret;
+  }
+  if (out_bits > 0)
+  {
+    WRITE_BITS_CHECKED_WITH_ACTION_ON_ERROR(out_data, (size_t)out_bits, out_bit_buf, options->error_log_file, free(out_data));
+  }
+  free(out_data);
+  return NO_ERROR;
+}
+
+/* ---- fused chains: one plugin = the whole DEGA chain ------------------------------------------------------ */
+/* `encode dega [adaptive] [valuesize=..] [normalization_factor=..]` == encode normalize # encode diff # encode seg # encode bac */
+io_int_t EncodeDEGA_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options)
+{
+  return RunStage(DC_STAGE_DEGA_ENC, in_bit_buf, out_bit_buf, options);
+}
+
+/* `decode dega ...` == decode bac # decode seg # decode diff # decode normalize */
+io_int_t DecodeDEGA_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options)
+{
+  return RunStage(DC_STAGE_DEGA_DEC, in_bit_buf, out_bit_buf, options);
+}
+
+/* ---- stage-by-stage plugins --------------------------------------------------------------------------------- */
+#ifdef DC_CUDA_REPLACE_REFERENCE
+  #define PLUGIN_NAME(cpu_name, gpu_name) cpu_name
+#else
+  #define PLUGIN_NAME(cpu_name, gpu_name) gpu_name
+#endif
+
+#define DEFINE_STAGE_PLUGIN(cpu_name, gpu_name, stage) \
+  io_int_t PLUGIN_NAME(cpu_name, gpu_name)(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options) \
+  { \
+    return RunStage((stage), in_bit_buf, out_bit_buf, options); \
+  }
+
+DEFINE_STAGE_PLUGIN(Normalize, Normalize_CUDA, DC_STAGE_NORMALIZE)                             /* normalize.c:9  */
+DEFINE_STAGE_PLUGIN(Denormalize, Denormalize_CUDA, DC_STAGE_DENORMALIZE)                       /* normalize.c:29 */
+DEFINE_STAGE_PLUGIN(EncodeDifferential, EncodeDifferential_CUDA, DC_STAGE_DIFF_ENC)            /* diff.c:9       */
+DEFINE_STAGE_PLUGIN(DecodeDifferential, DecodeDifferential_CUDA, DC_STAGE_DIFF_DEC)            /* diff.c:25      */
+DEFINE_STAGE_PLUGIN(EncodeSEG, EncodeSEG_CUDA, DC_STAGE_SEG_ENC)                               /* seg.c:31       */
+DEFINE_STAGE_PLUGIN(DecodeSEG, DecodeSEG_CUDA, DC_STAGE_SEG_DEC)                               /* seg.c:82       */
+DEFINE_STAGE_PLUGIN(EncodeBAC, EncodeBAC_CUDA, DC_STAGE_BAC_ENC)                               /* bac.c:147      */
+DEFINE_STAGE_PLUGIN(DecodeBAC, DecodeBAC_CUDA, DC_STAGE_BAC_DEC)                               /* bac.c:244      */
+DEFINE_STAGE_PLUGIN(EncodeLZMH, EncodeLZMH_CUDA, DC_STAGE_LZMH_ENC)                            /* lzmh.c:130     */
+DEFINE_STAGE_PLUGIN(DecodeLZMH, DecodeLZMH_CUDA, DC_STAGE_LZMH_DEC)                            /* lzmh.c:383     */

@@ -1,0 +1,66 @@
+"""Drop-in check at the reference's own front door: the unmodified DCCLI grammar, parameter parser, registry, csv
+codec and DCIOLib buffers (compiled from /root/reference into oracle/_ref/), with the five hot-path codecs
+replaced by data_compressor_b200/plugin/dc_cuda_plugin.c -> libdc_cuda.so.  Same command lines, same files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPU = os.path.join(ROOT, "oracle", "_ref", "DCCLI")
+GPU = os.path.join(ROOT, "oracle", "_ref", "DCCLI_cuda")
+
+
+def run(binary, src, dst, chain):
+    r = subprocess.run([binary, src, dst] + chain.split(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    return r.returncode
+
+
+@pytest.fixture(scope="module")
+def testfile(tmp_path_factory, golden):
+    if not (os.path.exists(CPU) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/DCCLI[_cuda] did not travel to this box")
+    d = tmp_path_factory.mktemp("dccli")
+    p = d / "input.txt"
+    # the reference's DCCLI/testdata/input.txt is one "%.2f" column; regenerate it from the committed float32 fixture
+    p.write_text("".join(f"{v:.2f}\n" for v in golden.testfile))
+    return d, str(p)
+
+
+DEGA = "decode csv # encode normalize # encode diff # encode seg # encode bac adaptive"
+UNDEGA = "decode bac adaptive # decode seg # decode diff # decode normalize # encode csv"
+
+
+@pytest.mark.parametrize("chain", [
+    DEGA,
+    "decode csv # encode normalize",                                        # A-XDR
+    "decode csv # encode normalize valuesize=24 # encode diff valuesize=24 # encode seg valuesize=24 # encode bac",
+    "encode lzmh",
+])
+def test_same_command_line_same_bytes(testfile, chain):
+    d, src = testfile
+    a, b = str(d / "cpu.bin"), str(d / "gpu.bin")
+    assert run(CPU, src, a, chain) == 0
+    assert run(GPU, src, b, chain) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_make_test_through_the_gpu_dccli(testfile):
+    """`make test` (DCCLI/build/gcc/Makefile:75-77): 10-stage DEGA round trip, then diff input output."""
+    d, src = testfile
+    out = str(d / "output.txt")
+    assert run(GPU, src, out, DEGA + " # " + UNDEGA) == 0
+    assert open(src, "rb").read() == open(out, "rb").read()
+
+
+def test_errors_propagate_like_the_reference(testfile):
+    d, src = testfile
+    neg = str(d / "neg.txt")
+    open(neg, "w").write("1.00\n-2.50\n3.00\n")
+    a, b = str(d / "e_cpu.bin"), str(d / "e_gpu.bin")
+    rc_cpu = run(CPU, neg, a, DEGA)
+    rc_gpu = run(GPU, neg, b, DEGA)
+    assert rc_cpu == rc_gpu != 0          # ERROR_LIBRARY_CALL as exit status (cli.c:447-453)
