@@ -104,17 +104,21 @@ struct BacModel
   }
 };
 
-// Interval after coding a symbol: LO0 (top-aligned lo), r1 (range).  Returns the E1/E2 count n1 and E3 count n3 and
-// leaves the renormalised interval in (LO, rng).  bac.c:112-137.
-__device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3)
+// Interval after coding a symbol: LO0 (top-aligned lo), r1 (range).  Returns the E1/E2 count n1, the E3 count n3 and
+// P1 = 2^n1, and leaves the renormalised interval in (LO, rng).  bac.c:112-137.
+//
+// Pipe balance: ncu shows this kernel bound by the integer ALU pipe (shifts, logic, compares) with the FMA pipe (IMAD)
+// two-thirds idle, so variable shifts are done as multiplications by 2^n wherever the product is needed anyway.
+__device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3, uint32_t &P1)
 {
   const uint32_t HI = LO0 + (r1 << 16) - 1;   // (hi << 16) | 0xFFFF
   n1 = clz_nz(LO0 ^ HI);                      // 0..16 (the low 16 bits of the xor are ones)
+  P1 = shl_c(1u, n1);                         // opaque to the optimiser: keeps the multiplications below
   const uint32_t z = ~LO0 | HI;               // clear exactly where lo has 1 and hi has 0
-  n3 = clz_nz((z << n1) << 1);                // run below the first differing bit, capped by the guard ones
-  const uint32_t n = n1 + n3;
-  rng = r1 << n;
-  LO = (LO0 << n) & 0x7FFF0000u;
+  n3 = clz_nz((z * P1) << 1);                 // run below the first differing bit, capped by the guard ones
+  const uint32_t Pn = shl_c(P1, n3);          // n1 + n3 <= 31
+  rng = r1 * Pn;
+  LO = (LO0 * Pn) & 0x7FFF0000u;
 }
 
 struct BacEncoder
@@ -130,19 +134,23 @@ struct BacEncoder
     pend = 0;
   }
 
-  // renormalise (LO0, r1) and emit (bac.c:112-137 + OutputNextBits, bac.c:93-105)
+  // renormalise (LO0, r1) and emit (bac.c:112-137 + OutputNextBits, bac.c:93-105).
+  // The writer's 64-bit accumulator may hold up to 64 bits here; the CALLER drains it (w.drain()) every few symbols,
+  // at a warp-uniform point, so that the data-dependent "word is full" branch is not taken per symbol.
   __device__ __forceinline__ void renorm_emit(uint32_t LO0, uint32_t r1, BitWriter &w)
   {
-    uint32_t n1, n3;
-    bac_renorm(LO0, r1, LO, rng, n1, n3);
+    uint32_t n1, n3, P1;
+    bac_renorm(LO0, r1, LO, rng, n1, n3, P1);
     const bool some = n1 != 0;
     const uint32_t k = some ? n1 + pend : 0u;   // bits leaving now: n1 plus the pending run spliced after the first
     const uint32_t p0 = pend;
     pend = (some ? 0u : pend) + n3;
-    // One rare region per symbol: the accumulator would reach a full word, or k > 32.
-    if (w.nacc + k >= 32)
+    // One rare region per symbol: k >= 32 (more than 16 consecutive E3 steps) or the accumulator would overflow
+    // (nacc + k > 64 with k < 32 implies k + nacc/2 > 33).
+    if (k + (w.nacc >> 1) >= 32)
     {
-      if (k > 32)   // practically never: more than 16 consecutive E3 steps before this E1/E2 step
+      w.drain();
+      if (k > 32)
       {
         const uint32_t first = LO0 >> 31;
         w.put(first, 1);
@@ -153,7 +161,9 @@ struct BacEncoder
         w.put(shr_c(LO0, 32 - n1) + shl_c(1u, k - 1) - shl_c(1u, n1 - 1), k);
       return;
     }
-    w.acc = (w.acc << k) | (shr_c(LO0, 32 - n1) + shl_c(1u, k - 1) - shl_c(1u, n1 - 1));
+    // top n1 bits of lo, with the pending run spliced in: bits + 2^(k-1) - 2^(n1-1); k <= 31 here
+    const uint32_t Pk = shl_c(1u, k);
+    w.acc = w.acc * Pk + (__umulhi(LO0, P1) + ((Pk - P1) >> 1));
     w.nacc += k;
   }
 
@@ -171,6 +181,7 @@ struct BacEncoder
   __device__ __forceinline__ void finish(const DivEntry e, BitWriter &w)
   {
     renorm_emit(LO, div_magic(rng, e), w);
+    w.drain();
     const uint32_t bit = LO < 0x40000000u ? 0u : 1u;
     w.put(bit, 1);
     w.run(bit ^ 1u, (uint64_t)pend + 1);

@@ -61,7 +61,14 @@ struct BitWriter
     nwords++;
   }
 
-  // n in [0, 32], v < 2^n
+  // brings nacc back below 32 (the arithmetic coder lets it grow up to 64 between warp-uniform drain points)
+  __device__ __forceinline__ void drain()
+  {
+    while (nacc >= 32)
+      flush_word();
+  }
+
+  // n in [0, 32], v < 2^n; requires nacc < 32
   __device__ __forceinline__ void put(uint32_t v, uint32_t n)
   {
     acc = (acc << n) | v;
