@@ -21,13 +21,23 @@ __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
     front_body(a, s);
 }
 
+__global__ void __launch_bounds__(128) front_dega_kernel(const FrontArgs a)
+{
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.lay.n_streams)
+    front_dega_body(a, s);
+}
+
 void launch_front(const FrontArgs &a, cudaStream_t st)
 {
   if (a.lay.n_streams == 0)
     return;
   const unsigned block = 128;
   const unsigned grid = (unsigned)((a.lay.n_streams + block - 1) / block);
-  front_kernel<<<grid, block, 0, st>>>(a);
+  if (a.in_is_float && a.do_norm && a.do_diff && a.out_seg)
+    front_dega_kernel<<<grid, block, 0, st>>>(a);
+  else
+    front_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;
 }
 
@@ -39,13 +49,23 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
     back_body(a, s);
 }
 
+__global__ void __launch_bounds__(128) back_dega_kernel(const BackArgs a)
+{
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.n_streams)
+    back_dega_body(a, s);
+}
+
 void launch_back(const BackArgs &a, cudaStream_t st)
 {
   if (a.n_streams == 0)
     return;
   const unsigned block = 128;
   const unsigned grid = (unsigned)((a.n_streams + block - 1) / block);
-  back_kernel<<<grid, block, 0, st>>>(a);
+  if (a.in_seg && a.do_undiff && a.do_denorm && a.vs >= 17)
+    back_dega_kernel<<<grid, block, 0, st>>>(a);
+  else
+    back_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;
 }
 

@@ -20,6 +20,10 @@
 #define __align__(x)
 
 typedef void *cudaStream_t;
+struct float4
+{
+  float x, y, z, w;
+};
 
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }

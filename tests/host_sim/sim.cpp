@@ -128,7 +128,10 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       fa.out.stride_bytes = stage == DC_STAGE_DEGA_ENC ? mid_cap : out_dev;
       fa.out.nbits = stage == DC_STAGE_DEGA_ENC ? &meta[1] : &meta[2];
       fa.status = status;
-      front_body(fa, 0);
+      if (fa.in_is_float && fa.do_norm && fa.do_diff && fa.out_seg)
+        front_dega_body(fa, 0);
+      else
+        front_body(fa, 0);
     }
     if (stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC || stage == DC_STAGE_BAC_DEC || stage == DC_STAGE_DEGA_DEC)
     {
@@ -188,7 +191,10 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       ka.out.nbits = &meta[2];
       ka.n_out = &meta[3];
       ka.status = status;
-      back_body(ka, 0);
+      if (ka.in_seg && ka.do_undiff && ka.do_denorm && ka.vs >= 17)
+        back_dega_body(ka, 0);
+      else
+        back_body(ka, 0);
     }
     if (meta[5] != 0 && boost < 4096)
       continue;
@@ -270,7 +276,7 @@ int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t ch
   uint64_t run = 0;
   for (uint64_t s = 0; s < n; s++)
   {
-    front_body(fa, s);
+    front_dega_body(fa, s);
     if (adaptive)
       bac_encode_body<true>(ba, s, div_table());
     else
@@ -336,7 +342,10 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
       bac_decode_body<true>(ba, s, div_table());
     else
       bac_decode_body<false>(ba, s, div_table());
-    back_body(ka, s);
+    if (vs >= 17)
+      back_dega_body(ka, s);
+    else
+      back_body(ka, s);
   }
   return DC_OK;
 }
