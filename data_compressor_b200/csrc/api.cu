@@ -229,6 +229,92 @@ int read_back(dc_ctx *c, const uint64_t *d_src, uint64_t *dst, int count)
   return DC_OK;
 }
 
+// ---- A-XDR fast path: equal-length streams, records that are whole 32-bit words -------------------------------
+bool axdr_eligible(const Layout &L, uint32_t vs, uint64_t &len)
+{
+  if (L.sample_off != nullptr || L.n_streams == 0 || L.channel_len == 0)
+    return false;
+  if (L.channel_len % L.block_len != 0 && L.blocks_per_channel != 1)
+    return false;
+  len = L.blocks_per_channel == 1 ? L.channel_len : L.block_len;
+  return (len * vs) % 32 == 0;
+}
+
+int axdr_fast_encode(dc_ctx *c, const float *d_samples, const Layout &L, const dc_params *p, uint8_t *d_payload, uint64_t payload_cap,
+                     uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status, uint64_t *total_bytes)
+{
+  uint64_t len;
+  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 3) != 0)
+    return DC_ERR_INVALID_MODE;
+  const uint64_t wps = len * p->value_size_bits / 32;
+  const uint64_t tot = L.n_streams * wps * 4;
+  if (total_bytes)
+    *total_bytes = tot;
+  if (tot > payload_cap)
+  {
+    set_err(c, "payload needs %llu bytes, capacity is %llu", (unsigned long long)tot, (unsigned long long)payload_cap);
+    return DC_ERR_MEMORY;
+  }
+  int rc = arena_reserve(c, 4096);
+  if (rc != DC_OK)
+    return rc;
+  c->ev_mask = 0;
+  unsigned long long *d_flag = reinterpret_cast<unsigned long long *>(c->arena);
+  CU_TRY(c, cudaMemsetAsync(d_flag, 0, sizeof(unsigned long long), c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemsetAsync(d_status, 0, L.n_streams * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
+  AxdrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_streams = L.n_streams;
+  a.len = len;
+  a.words_per_stream = wps;
+  a.vs = p->value_size_bits;
+  a.nf = p->normalization_factor;
+  a.samples_in = d_samples;
+  a.payload_words = reinterpret_cast<uint32_t *>(d_payload);
+  a.bit_len = d_bit_len;
+  a.byte_off = d_byte_off;
+  a.status = d_status;
+  a.err_flag = d_flag;
+  {
+    Timed t(c, DC_K_FRONT);
+    launch_axdr_encode(a, c->stream);
+  }
+  if ((rc = check_launch(c, "axdr_encode_kernel")) != DC_OK)
+    return rc;
+  uint64_t flag = 0;
+  if ((rc = read_back(c, reinterpret_cast<const uint64_t *>(d_flag), &flag, 1)) != DC_OK)
+    return rc;
+  return flag ? DC_ERR_INVALID_MODE : DC_OK;   // a failed stream changes the dense layout: redo on the general path
+}
+
+int axdr_fast_decode(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes, const Layout &L, const dc_params *p, float *d_samples,
+                     uint64_t *d_n_out, int32_t *d_status)
+{
+  uint64_t len;
+  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 3) != 0)
+    return DC_ERR_INVALID_MODE;
+  const uint64_t wps = len * p->value_size_bits / 32;
+  if (payload_bytes != L.n_streams * wps * 4)   // not the dense equal-length layout (e.g. failed streams): general path
+    return DC_ERR_INVALID_MODE;
+  c->ev_mask = 0;
+  AxdrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_streams = L.n_streams;
+  a.len = len;
+  a.words_per_stream = wps;
+  a.vs = p->value_size_bits;
+  a.nf = p->normalization_factor;
+  a.samples_out = d_samples;
+  a.payload = d_payload;
+  a.n_out = d_n_out;
+  a.status = d_status;
+  {
+    Timed t(c, DC_K_BACK);
+    launch_axdr_decode(a, c->stream);
+  }
+  return check_launch(c, "axdr_decode_kernel");
+}
+
 // ---- encode pipeline: front end -> [bac] -> scan -> gather ----------------------------------------------
 enum FrontKind { FRONT_DEGA, FRONT_AXDR };
 
@@ -557,6 +643,12 @@ static int encode_device_common(dc_ctx *c, FrontKind kind, const float *d_sample
   const int rc = make_layout(c, layout, layout->sample_off ? host_off.data() : nullptr, L, max_len, total);
   if (rc != DC_OK)
     return rc;
+  if (kind == FRONT_AXDR)
+  {
+    const int frc = axdr_fast_encode(c, d_samples, L, params, d_payload, payload_cap, d_bit_len, d_byte_off, d_status, total_bytes);
+    if (frc != DC_ERR_INVALID_MODE)   // INVALID_MODE = layout not eligible (or a sample failed): take the general path
+      return frc;
+  }
   return encode_pipeline(c, kind, d_samples, L, max_len, params, d_payload, payload_cap, d_bit_len, d_byte_off, d_status, total_bytes);
 }
 
@@ -564,7 +656,6 @@ static int decode_device_common(dc_ctx *c, FrontKind kind, const uint8_t *d_payl
                                 const uint64_t *d_byte_off, const dc_layout *layout, const dc_params *params, float *d_samples,
                                 uint64_t *d_n_out, int32_t *d_status)
 {
-  (void)payload_bytes;
   if (!c || !params_ok(params) || !layout || !d_bit_len || !d_byte_off || !d_n_out || !d_status)
     return DC_ERR_INVALID_VALUE;
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
@@ -580,6 +671,12 @@ static int decode_device_common(dc_ctx *c, FrontKind kind, const uint8_t *d_payl
   const int rc = make_layout(c, layout, layout->sample_off ? host_off.data() : nullptr, L, max_len, total);
   if (rc != DC_OK)
     return rc;
+  if (kind == FRONT_AXDR)
+  {
+    const int frc = axdr_fast_decode(c, d_payload, payload_bytes, L, params, d_samples, d_n_out, d_status);
+    if (frc != DC_ERR_INVALID_MODE)
+      return frc;
+  }
   return decode_pipeline(c, kind, d_payload, d_bit_len, d_byte_off, L, max_len, params, d_samples, d_n_out, d_status);
 }
 

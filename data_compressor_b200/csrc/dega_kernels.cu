@@ -70,6 +70,106 @@ void launch_back(const BackArgs &a, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// A-XDR fast path (normalize only, normalize.c:9-42) for equal-length streams with word-aligned records.
+// Memory bound: 4 B read + vs/8 B written per sample, every access coalesced.
+__global__ void __launch_bounds__(256) axdr_encode_kernel(const AxdrArgs a)
+{
+  const uint32_t vs = a.vs;
+  const uint64_t mask = low_mask(vs);
+  const float lo_bound = -(float)(1ull << (vs - 1));
+  const float hi_bound = (float)((1ull << (vs - 1)) - 1);
+  const uint64_t total_words = a.n_streams * a.words_per_stream;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_words; g += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint64_t s = g / a.words_per_stream;
+    const uint64_t wi = g - s * a.words_per_stream;
+    const uint64_t bit0 = wi * 32;
+    const float *src = a.samples_in + s * a.len;
+    uint32_t word = 0;
+    bool ok = true;
+    // every vs-bit field that overlaps stream bits [bit0, bit0 + 32)
+    for (uint64_t i = bit0 / vs; i * vs < bit0 + 32 && i < a.len; i++)
+    {
+      int64_t n;
+      if (!normalize_one(__ldg(src + i), a.nf, lo_bound, hi_bound, n))
+      {
+        ok = false;
+        break;
+      }
+      const uint64_t u = (uint64_t)n & mask;
+      const int64_t shift = (int64_t)(i * vs + vs) - (int64_t)(bit0 + 32);   // > 0: the field ends after this word
+      word |= shift >= 0 ? (uint32_t)(u >> shift) : (uint32_t)(u << (-shift));
+    }
+    if (!ok)
+    {
+      a.status[s] = DC_ERR_INVALID_VALUE_D;
+      atomicExch(a.err_flag, 1ull);
+    }
+    a.payload_words[g] = bswap32(word);
+    if (wi == 0)
+    {
+      a.bit_len[s] = a.len * vs;
+      a.byte_off[s] = s * a.words_per_stream * 4;
+      if (s == a.n_streams - 1)
+        a.byte_off[a.n_streams] = a.n_streams * a.words_per_stream * 4;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) axdr_decode_kernel(const AxdrArgs a)
+{
+  const uint32_t vs = a.vs;
+  const uint64_t mask = low_mask(vs);
+  const uint64_t total = a.n_streams * a.len;
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(a.payload);
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint64_t s = g / a.len;
+    const uint64_t i = g - s * a.len;
+    const uint64_t bit = i * vs;
+    const uint32_t *w = words + s * a.words_per_stream + (bit >> 5);
+    const uint32_t sh = (uint32_t)(bit & 31);
+    // up to 96 stream bits starting at a word boundary cover any field of at most 64 bits
+    const uint64_t w0 = bswap32(__ldg(w));
+    const uint64_t w1 = sh + vs > 32 ? bswap32(__ldg(w + 1)) : 0;
+    const uint64_t w2 = sh + vs > 64 ? bswap32(__ldg(w + 2)) : 0;
+    const uint64_t hi = (w0 << 32) | w1;           // stream bits [0, 64) from the word boundary
+    uint64_t u = sh ? ((hi << sh) | (w2 << 32 >> (64 - sh))) : hi;   // field left-aligned
+    u = (u >> (64 - vs)) & mask;
+    a.samples_out[g] = __fdiv_rn(__ll2float_rn(sext(u, vs)), a.nf);   // normalize.c:36-39
+    if (i == 0)
+    {
+      a.n_out[s] = a.len;
+      a.status[s] = 0;
+    }
+  }
+}
+
+void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
+{
+  const uint64_t total = a.n_streams * a.words_per_stream;
+  if (total == 0)
+    return;
+  const unsigned block = 256;
+  const uint64_t want = (total + block - 1) / block;
+  const unsigned grid = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);   // grid-stride: 32 CTAs of 256 per SM slot
+  axdr_encode_kernel<<<grid, block, 0, st>>>(a);
+  g_launches++;
+}
+
+void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
+{
+  const uint64_t total = a.n_streams * a.len;
+  if (total == 0)
+    return;
+  const unsigned block = 256;
+  const uint64_t want = (total + block - 1) / block;
+  const unsigned grid = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
+  axdr_decode_kernel<<<grid, block, 0, st>>>(a);
+  g_launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Arithmetic coder kernels.  The 128 KiB division table lives in shared memory (one copy per CTA, one CTA of
 // kBacThreads threads per SM); before the first halving every lane of a warp has coded the same number of
 // symbols, so `total` is warp-uniform and the table read is a broadcast.

@@ -62,6 +62,28 @@ struct FrontArgs
 };
 void launch_front(const FrontArgs &a, cudaStream_t st);
 
+// ---- A-XDR fast path: equal-length streams whose records are whole 32-bit words ------------------------------
+// One thread per 32-bit output word (encode) / per sample (decode): fully coalesced, no scratch, no scan, no gather.
+struct AxdrArgs
+{
+  uint64_t n_streams;
+  uint64_t len;              // samples per stream
+  uint64_t words_per_stream; // len * vs / 32
+  uint32_t vs;
+  float nf;
+  const float *samples_in;   // encode
+  float *samples_out;        // decode
+  uint32_t *payload_words;   // encode: dense payload (4-byte aligned)
+  const uint8_t *payload;    // decode
+  uint64_t *bit_len;         // encode out
+  uint64_t *byte_off;        // encode out [n+1]
+  uint64_t *n_out;           // decode out
+  int32_t *status;
+  unsigned long long *err_flag;   // encode: set when any sample fails the range check (caller falls back)
+};
+void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st);
+void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st);
+
 // ---- back end: {seg parse | fixed-width unpack} -> [undiff] -> [denormalize] ------------------------
 struct BackArgs
 {

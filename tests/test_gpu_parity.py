@@ -181,6 +181,31 @@ def test_axdr_normalize_only(ctx, oracle):
         assert torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
 
 
+def test_axdr_failed_meter_falls_back_to_dense_layout(ctx, oracle):
+    rng = np.random.default_rng(6)
+    x = profile(rng, (40, 96), step=40, base=500)
+    x[7, 13] = 5.0e9                       # normalize rejects this meter (normalize.c:21-22)
+    enc = ctx.axdr_encode(torch.from_numpy(x).cuda(), vs=32)
+    st = enc.status.cpu().tolist()
+    assert st[7] == -1 and sum(1 for v in st if v) == 1 and int(enc.bit_len[7]) == 0
+    assert enc.total_bytes == 39 * 96 * 4
+    for s in (0, 6, 8, 39):
+        assert enc.stream_bytes(s) == oracle.run_chain([ob.NORMALIZE], x[s], 96 * 32, 32)[1]
+
+
+def test_axdr_million_meters_round_trip(ctx, oracle):
+    """BASELINE.json config 3 at full size: 1,000,000 meters x 96 samples, normalize only."""
+    from data_compressor_b200 import synth
+    x = synth.meters_15min(1_000_000, 96, device="cuda")
+    for vs in (32, 24):
+        enc = ctx.axdr_encode(x, vs=vs)
+        assert enc.total_bytes == 1_000_000 * 96 * vs // 8 and not enc.status.any().item()
+        y, n_out, status = ctx.axdr_decode(enc, vs=vs)
+        assert torch.equal(y.view(torch.int32), x.view(torch.int32))
+        for s in (0, 123_456, 999_999):
+            assert enc.stream_bytes(s) == oracle.run_chain([ob.NORMALIZE], x[s].cpu().numpy(), 96 * 32, vs)[1]
+
+
 # ---- LZMH ------------------------------------------------------------------------------------------------------
 def test_lzmh_golden_vectors(ctx, golden):
     for name in golden.names:
