@@ -244,7 +244,7 @@ int axdr_fast_encode(dc_ctx *c, const float *d_samples, const Layout &L, const d
                      uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status, uint64_t *total_bytes)
 {
   uint64_t len;
-  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 3) != 0)
+  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 15) != 0)
     return DC_ERR_INVALID_MODE;
   const uint64_t wps = len * p->value_size_bits / 32;
   const uint64_t tot = L.n_streams * wps * 4;
@@ -291,7 +291,8 @@ int axdr_fast_decode(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes
                      uint64_t *d_n_out, int32_t *d_status)
 {
   uint64_t len;
-  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 3) != 0)
+  if (!axdr_eligible(L, p->value_size_bits, len) || (reinterpret_cast<uintptr_t>(d_payload) & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(d_samples) & 15) != 0)
     return DC_ERR_INVALID_MODE;
   const uint64_t wps = len * p->value_size_bits / 32;
   if (payload_bytes != L.n_streams * wps * 4)   // not the dense equal-length layout (e.g. failed streams): general path

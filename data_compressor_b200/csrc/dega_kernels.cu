@@ -72,99 +72,194 @@ void launch_back(const BackArgs &a, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------------------
 // A-XDR fast path (normalize only, normalize.c:9-42) for equal-length streams with word-aligned records.
 // Memory bound: 4 B read + vs/8 B written per sample, every access coalesced.
+// One 32-bit word of a record: every vs-bit field overlapping stream bits [32*wi, 32*wi + 32)
+__device__ __forceinline__ uint32_t axdr_word(const float *src, uint32_t len, uint32_t wi, uint32_t vs, uint64_t mask, float nf, float lo_bound,
+                                              float hi_bound, bool &ok)
+{
+  const uint32_t bit0 = wi * 32;
+  uint32_t word = 0;
+  for (uint32_t i = bit0 / vs; i * vs < bit0 + 32 && i < len; i++)
+  {
+    int64_t n;
+    if (!normalize_one(__ldg(src + i), nf, lo_bound, hi_bound, n))
+    {
+      ok = false;
+      return 0;
+    }
+    const uint64_t u = (uint64_t)n & mask;
+    const int shift = (int)(i * vs + vs) - (int)(bit0 + 32);   // > 0: the field ends after this word
+    word |= shift >= 0 ? (uint32_t)(u >> shift) : (uint32_t)(u << (-shift));
+  }
+  return bswap32(word);
+}
+
+// Four consecutive output words per thread (one 128-bit store).  VS32: a word is exactly one sample, so the four
+// inputs come from one 128-bit load.
+template <bool VS32>
 __global__ void __launch_bounds__(256) axdr_encode_kernel(const AxdrArgs a)
 {
   const uint32_t vs = a.vs;
   const uint64_t mask = low_mask(vs);
   const float lo_bound = -(float)(1ull << (vs - 1));
   const float hi_bound = (float)((1ull << (vs - 1)) - 1);
+  const uint32_t wps = (uint32_t)a.words_per_stream, len = (uint32_t)a.len;
   const uint64_t total_words = a.n_streams * a.words_per_stream;
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_words; g += (uint64_t)gridDim.x * blockDim.x)
+  const uint64_t total_quads = (total_words + 3) / 4;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (uint64_t)gridDim.x * blockDim.x)
   {
-    const uint64_t s = g / a.words_per_stream;
-    const uint64_t wi = g - s * a.words_per_stream;
-    const uint64_t bit0 = wi * 32;
-    const float *src = a.samples_in + s * a.len;
-    uint32_t word = 0;
+    const uint64_t g = q * 4;
+    uint64_t s = g / wps;
+    uint32_t wi = (uint32_t)(g - s * wps);
+    uint32_t out[4];
     bool ok = true;
-    // every vs-bit field that overlaps stream bits [bit0, bit0 + 32)
-    for (uint64_t i = bit0 / vs; i * vs < bit0 + 32 && i < a.len; i++)
+    if (VS32 && g + 4 <= total_words)
     {
-      int64_t n;
-      if (!normalize_one(__ldg(src + i), a.nf, lo_bound, hi_bound, n))
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(a.samples_in + g));   // wps == len: same flat index
+      const float f[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int j = 0; j < 4; j++)
       {
-        ok = false;
-        break;
+        int64_t n = 0;
+        const bool okj = normalize_one(f[j], a.nf, lo_bound, hi_bound, n);
+        out[j] = bswap32((uint32_t)((uint64_t)n & mask));
+        if (!okj)
+        {
+          a.status[(g + j) / wps] = DC_ERR_INVALID_VALUE_D;
+          ok = false;
+        }
       }
-      const uint64_t u = (uint64_t)n & mask;
-      const int64_t shift = (int64_t)(i * vs + vs) - (int64_t)(bit0 + 32);   // > 0: the field ends after this word
-      word |= shift >= 0 ? (uint32_t)(u >> shift) : (uint32_t)(u << (-shift));
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        out[j] = 0;
+        if (g + j < total_words)
+        {
+          bool okj = true;
+          out[j] = axdr_word(a.samples_in + s * len, len, wi, vs, mask, a.nf, lo_bound, hi_bound, okj);
+          if (!okj)
+          {
+            a.status[s] = DC_ERR_INVALID_VALUE_D;
+            ok = false;
+          }
+          if (wi == 0)
+          {
+            a.bit_len[s] = (uint64_t)len * vs;
+            a.byte_off[s] = s * wps * 4ull;
+          }
+          if (++wi == wps)
+          {
+            wi = 0;
+            s++;
+          }
+        }
+      }
+    }
+    if (VS32 && g + 4 <= total_words)   // index arrays for the vector path: a stream starts inside this quad at most once per wps words
+    {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        if (wi == 0)
+        {
+          a.bit_len[s] = (uint64_t)len * vs;
+          a.byte_off[s] = s * wps * 4ull;
+        }
+        if (++wi == wps)
+        {
+          wi = 0;
+          s++;
+        }
+      }
     }
     if (!ok)
-    {
-      a.status[s] = DC_ERR_INVALID_VALUE_D;
       atomicExch(a.err_flag, 1ull);
-    }
-    a.payload_words[g] = bswap32(word);
-    if (wi == 0)
-    {
-      a.bit_len[s] = a.len * vs;
-      a.byte_off[s] = s * a.words_per_stream * 4;
-      if (s == a.n_streams - 1)
-        a.byte_off[a.n_streams] = a.n_streams * a.words_per_stream * 4;
-    }
+    if (g + 4 <= total_words)
+      *reinterpret_cast<uint4 *>(a.payload_words + g) = make_uint4(out[0], out[1], out[2], out[3]);
+    else
+      for (int j = 0; j < 4 && g + j < total_words; j++)
+        a.payload_words[g + j] = out[j];
+    if (q == 0)
+      a.byte_off[a.n_streams] = total_words * 4ull;
   }
 }
 
+// Four consecutive samples per thread (one 128-bit store)
 __global__ void __launch_bounds__(256) axdr_decode_kernel(const AxdrArgs a)
 {
   const uint32_t vs = a.vs;
   const uint64_t mask = low_mask(vs);
+  const uint32_t len = (uint32_t)a.len, wps = (uint32_t)a.words_per_stream;
   const uint64_t total = a.n_streams * a.len;
   const uint32_t *words = reinterpret_cast<const uint32_t *>(a.payload);
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x)
+  const uint64_t total_quads = (total + 3) / 4;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (uint64_t)gridDim.x * blockDim.x)
   {
-    const uint64_t s = g / a.len;
-    const uint64_t i = g - s * a.len;
-    const uint64_t bit = i * vs;
-    const uint32_t *w = words + s * a.words_per_stream + (bit >> 5);
-    const uint32_t sh = (uint32_t)(bit & 31);
-    // up to 96 stream bits starting at a word boundary cover any field of at most 64 bits
-    const uint64_t w0 = bswap32(__ldg(w));
-    const uint64_t w1 = sh + vs > 32 ? bswap32(__ldg(w + 1)) : 0;
-    const uint64_t w2 = sh + vs > 64 ? bswap32(__ldg(w + 2)) : 0;
-    const uint64_t hi = (w0 << 32) | w1;           // stream bits [0, 64) from the word boundary
-    uint64_t u = sh ? ((hi << sh) | (w2 << 32 >> (64 - sh))) : hi;   // field left-aligned
-    u = (u >> (64 - vs)) & mask;
-    a.samples_out[g] = __fdiv_rn(__ll2float_rn(sext(u, vs)), a.nf);   // normalize.c:36-39
-    if (i == 0)
+    const uint64_t g = q * 4;
+    uint64_t s = g / len;
+    uint32_t i = (uint32_t)(g - s * len);
+    float f[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+#pragma unroll
+    for (int j = 0; j < 4; j++)
     {
-      a.n_out[s] = a.len;
-      a.status[s] = 0;
+      if (g + j < total)
+      {
+        const uint32_t bit = i * vs;
+        const uint32_t *w = words + s * wps + (bit >> 5);
+        const uint32_t sh = bit & 31;
+        // up to 96 stream bits starting at a word boundary cover any field of at most 64 bits
+        const uint64_t w0 = bswap32(__ldg(w));
+        const uint64_t w1 = sh + vs > 32 ? bswap32(__ldg(w + 1)) : 0;
+        const uint64_t w2 = sh + vs > 64 ? bswap32(__ldg(w + 2)) : 0;
+        const uint64_t hi = (w0 << 32) | w1;
+        uint64_t u = sh ? ((hi << sh) | (w2 >> (32 - sh))) : hi;   // field left-aligned
+        u = (u >> (64 - vs)) & mask;
+        f[j] = __fdiv_rn(__ll2float_rn(sext(u, vs)), a.nf);   // normalize.c:36-39
+        if (i == 0)
+        {
+          a.n_out[s] = len;
+          a.status[s] = 0;
+        }
+        if (++i == len)
+        {
+          i = 0;
+          s++;
+        }
+      }
     }
+    if (g + 4 <= total)
+      *reinterpret_cast<float4 *>(a.samples_out + g) = make_float4(f[0], f[1], f[2], f[3]);
+    else
+      for (int j = 0; j < 4 && g + j < total; j++)
+        a.samples_out[g + j] = f[j];
   }
 }
 
 void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
 {
-  const uint64_t total = a.n_streams * a.words_per_stream;
+  const uint64_t total = (a.n_streams * a.words_per_stream + 3) / 4;
   if (total == 0)
     return;
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
-  const unsigned grid = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);   // grid-stride: 32 CTAs of 256 per SM slot
-  axdr_encode_kernel<<<grid, block, 0, st>>>(a);
+  const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);   // grid-stride over a multiple of the SM count
+  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0)
+    axdr_encode_kernel<true><<<grid, block, 0, st>>>(a);
+  else
+    axdr_encode_kernel<false><<<grid, block, 0, st>>>(a);
   g_launches++;
 }
 
 void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
 {
-  const uint64_t total = a.n_streams * a.len;
+  const uint64_t total = (a.n_streams * a.len + 3) / 4;
   if (total == 0)
     return;
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
-  const unsigned grid = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
+  const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
   axdr_decode_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;
 }
