@@ -25,6 +25,8 @@ struct dc_ctx
   uint64_t arena_size;
   uint8_t *stage;        // device staging of the host-buffer calls (samples, payload, index), grown on demand
   uint64_t stage_size;
+  cudaStream_t s_h2d, s_d2h;          // copy engines of the host-buffer calls (overlap with the compute stream)
+  cudaEvent_t ev_in[8], ev_out[8];    // per-chunk "input landed" / "results ready"
   uint64_t *h_pinned;   // small pinned mailbox for device->host scalars
   uint64_t launches_base;
   int profiling;
@@ -548,6 +550,17 @@ int dc_create(dc_ctx **out, int device)
       dc_destroy(c);
       return DC_ERR_LIBRARY_INIT;
     }
+  bool aux_ok = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 8 && aux_ok; i++)
+    aux_ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!aux_ok)
+  {
+    cudaGetLastError();
+    dc_destroy(c);
+    return DC_ERR_LIBRARY_INIT;
+  }
   c->launches_base = launch_counter();
   *out = c;
   return DC_OK;
@@ -571,6 +584,17 @@ void dc_destroy(dc_ctx *c)
   for (int i = 0; i < 2 * DC_K_COUNT; i++)
     if (c->ev[i])
       cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 8; i++)
+  {
+    if (c->ev_in[i])
+      cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_out[i])
+      cudaEventDestroy(c->ev_out[i]);
+  }
+  if (c->s_h2d)
+    cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h)
+    cudaStreamDestroy(c->s_d2h);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -712,6 +736,21 @@ int dc_axdr_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_
 }
 
 // ---- DEGA, host buffers ----------------------------------------------------------------------------------
+// Channel chunks of the host-buffer calls: the copy of chunk k+1 (and the copy-back of chunk k-1) overlaps the kernels
+// of chunk k.  A chunk keeps at least one full wave of coder CTAs (148 SMs x 1024 streams); ragged layouts use one.
+static int host_chunks(const Layout &L, uint64_t n_channels)
+{
+  if (L.sample_off != nullptr || n_channels < 2)
+    return 1;
+  const uint64_t wave = 148ull * 1024;
+  uint64_t k = L.n_streams / wave;
+  if (k > 8)
+    k = 8;
+  if (k > n_channels)
+    k = n_channels;
+  return k < 1 ? 1 : (int)k;
+}
+
 int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout, const dc_params *params, uint8_t *payload,
                         uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes)
 {
@@ -724,40 +763,100 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
   if (rc != DC_OK)
     return rc;
   const uint64_t n = L.n_streams;
-  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_cap, 4) + 16, 1) + Bump::size_of(n, 8) +
-                        2 * Bump::size_of(n + 1, 8) + Bump::size_of(n, 4) + 4096;
+  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_cap, 4) + 256, 1) + Bump::size_of(n, 8) +
+                        2 * Bump::size_of(n + 8, 8) + Bump::size_of(n, 4) + 4096;
   if ((rc = stage_reserve(c, need)) != DC_OK)
     return rc;
   Bump b(c->stage);
   float *d_samples = b.take<float>(total);
-  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_cap, 4) + 16);
+  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_cap, 4) + 256);
   uint64_t *d_bits = b.take<uint64_t>(n);
-  uint64_t *d_boff = b.take<uint64_t>(n + 1);
-  uint64_t *d_off = b.take<uint64_t>(n + 1);
+  uint64_t *d_boff = b.take<uint64_t>(n + 8);
+  uint64_t *d_off = b.take<uint64_t>(n + 8);
   int32_t *d_status = b.take<int32_t>(n);
   if (layout->sample_off)
   {
     CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
     L.sample_off = d_off;
   }
-  if (total)
-    CU_TRY(c, cudaMemcpyAsync(d_samples, samples, total * 4, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  uint64_t tot = 0;
-  rc = encode_pipeline(c, FRONT_DEGA, d_samples, L, max_len, params, d_payload, payload_cap, d_bits, d_boff, d_status, &tot);
-  if (total_bytes)
-    *total_bytes = tot;
-  if (rc != DC_OK && rc != DC_ERR_MEMORY)
+  const int n_chunks = host_chunks(L, layout->n_channels);
+  const uint64_t ch_per = layout->sample_off ? 0 : (layout->n_channels + n_chunks - 1) / n_chunks;
+  const uint64_t bpc = L.blocks_per_channel;
+  // the staging block may have been read by the previous call's copy-back: order the new copies after it
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
+  auto chunk_range = [&](int k, uint64_t &c0, uint64_t &c1) {
+    if (n_chunks == 1)
+    {
+      c0 = 0;
+      c1 = layout->sample_off ? 0 : layout->n_channels;
+      return;
+    }
+    c0 = std::min<uint64_t>((uint64_t)k * ch_per, layout->n_channels);
+    c1 = std::min<uint64_t>(c0 + ch_per, layout->n_channels);
+  };
+  auto upload = [&](int k) -> int {
+    uint64_t c0, c1;
+    chunk_range(k, c0, c1);
+    const uint64_t first = n_chunks == 1 ? 0 : c0 * L.channel_len;
+    const uint64_t count = n_chunks == 1 ? total : (c1 - c0) * L.channel_len;
+    if (count)
+      CU_TRY(c, cudaMemcpyAsync(d_samples + first, samples + first, count * 4, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaEventRecord(c->ev_in[k], c->s_h2d), DC_ERR_LIBRARY_CALL);
+    return DC_OK;
+  };
+  uint64_t base = 0;   // payload bytes of the chunks before this one
+  uint64_t chunk_base[8], chunk_first[8], chunk_count[8];
+  int result = DC_OK;
+  if ((rc = upload(0)) != DC_OK)
     return rc;
-  if (bit_len && n)
-    CU_TRY(c, cudaMemcpyAsync(bit_len, d_bits, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  for (int k = 0; k < n_chunks; k++)
+  {
+    if (k + 1 < n_chunks && (rc = upload(k + 1)) != DC_OK)
+      return rc;
+    uint64_t c0, c1;
+    chunk_range(k, c0, c1);
+    Layout Lk = L;
+    const uint64_t s0 = n_chunks == 1 ? 0 : c0 * bpc;
+    if (n_chunks > 1)
+      Lk.n_streams = (c1 - c0) * bpc;
+    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
+    uint64_t tot = 0;
+    const uint64_t cap_left = payload_cap > base ? payload_cap - base : 0;
+    // chunk payloads start 16-byte aligned on the device; the host copy below packs them densely
+    const uint64_t dev_base = round_up(base, 16);
+    rc = encode_pipeline(c, FRONT_DEGA, d_samples + (n_chunks == 1 ? 0 : c0 * L.channel_len), Lk, max_len, params, d_payload + dev_base,
+                         cap_left, d_bits + s0, d_boff + s0, d_status + s0, &tot);
+    if (rc != DC_OK && rc != DC_ERR_MEMORY)
+      return rc;
+    if (rc == DC_ERR_MEMORY)
+      result = rc;
+    const uint64_t nk = Lk.n_streams;
+    // encode_pipeline has synchronised the compute stream: the chunk's results are complete
+    if (bit_len && nk)
+      CU_TRY(c, cudaMemcpyAsync(bit_len + s0, d_bits + s0, nk * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    if (byte_off && nk)
+      CU_TRY(c, cudaMemcpyAsync(byte_off + s0, d_boff + s0, nk * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    if (status && nk)
+      CU_TRY(c, cudaMemcpyAsync(status + s0, d_status + s0, nk * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    if (result == DC_OK && payload && tot)
+      CU_TRY(c, cudaMemcpyAsync(payload + base, d_payload + dev_base, tot, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    chunk_base[k] = base;
+    chunk_first[k] = s0;
+    chunk_count[k] = nk;
+    base += tot;
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
   if (byte_off)
-    CU_TRY(c, cudaMemcpyAsync(byte_off, d_boff, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (status && n)
-    CU_TRY(c, cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (rc == DC_OK && payload && tot)
-    CU_TRY(c, cudaMemcpyAsync(payload, d_payload, tot, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
-  return rc;
+  {
+    // chunk-local offsets become container offsets (chunk 0 already is)
+    for (int k = 1; k < n_chunks; k++)
+      for (uint64_t i = 0; i < chunk_count[k]; i++)
+        byte_off[chunk_first[k] + i] += chunk_base[k];
+    byte_off[n] = base;
+  }
+  if (total_bytes)
+    *total_bytes = base;
+  return result;
 }
 
 int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_bytes, const uint64_t *bit_len, const uint64_t *byte_off,
@@ -784,25 +883,72 @@ int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_byte
   uint64_t *d_boff = b.take<uint64_t>(n + 1);
   uint64_t *d_off = b.take<uint64_t>(n + 1);
   int32_t *d_status = b.take<int32_t>(n);
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
   if (layout->sample_off)
   {
-    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
     L.sample_off = d_off;
   }
-  if (payload_bytes)
-    CU_TRY(c, cudaMemcpyAsync(d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  // index first (small), then the payload chunk by chunk at its container offset
   if (n)
-    CU_TRY(c, cudaMemcpyAsync(d_bits, bit_len, n * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaMemcpyAsync(d_boff, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-  rc = decode_pipeline(c, FRONT_DEGA, d_payload, d_bits, d_boff, L, max_len, params, d_samples, d_nout, d_status);
-  if (rc != DC_OK)
+    CU_TRY(c, cudaMemcpyAsync(d_bits, bit_len, n * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemcpyAsync(d_boff, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+  const int n_chunks = host_chunks(L, layout->n_channels);
+  const uint64_t ch_per = layout->sample_off ? 0 : (layout->n_channels + n_chunks - 1) / n_chunks;
+  const uint64_t bpc = L.blocks_per_channel;
+  auto chunk_streams = [&](int k, uint64_t &s0, uint64_t &s1, uint64_t &c0, uint64_t &c1) {
+    if (n_chunks == 1)
+    {
+      s0 = 0;
+      s1 = n;
+      c0 = 0;
+      c1 = layout->n_channels;
+      return;
+    }
+    c0 = std::min<uint64_t>((uint64_t)k * ch_per, layout->n_channels);
+    c1 = std::min<uint64_t>(c0 + ch_per, layout->n_channels);
+    s0 = c0 * bpc;
+    s1 = c1 * bpc;
+  };
+  auto upload = [&](int k) -> int {
+    uint64_t s0, s1, c0, c1;
+    chunk_streams(k, s0, s1, c0, c1);
+    const uint64_t b0 = byte_off[s0], b1 = byte_off[s1];
+    if (b1 < b0 || b1 > payload_bytes)
+      return DC_ERR_INVALID_VALUE;
+    if (b1 > b0)
+      CU_TRY(c, cudaMemcpyAsync(d_payload + b0, payload + b0, b1 - b0, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaEventRecord(c->ev_in[k], c->s_h2d), DC_ERR_LIBRARY_CALL);
+    return DC_OK;
+  };
+  if ((rc = upload(0)) != DC_OK)
     return rc;
-  if (samples && total)
-    CU_TRY(c, cudaMemcpyAsync(samples, d_samples, total * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (n_out && n)
-    CU_TRY(c, cudaMemcpyAsync(n_out, d_nout, n * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
-  if (status && n)
-    CU_TRY(c, cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  for (int k = 0; k < n_chunks; k++)
+  {
+    if (k + 1 < n_chunks && (rc = upload(k + 1)) != DC_OK)
+      return rc;
+    uint64_t s0, s1, c0, c1;
+    chunk_streams(k, s0, s1, c0, c1);
+    Layout Lk = L;
+    if (n_chunks > 1)
+      Lk.n_streams = s1 - s0;
+    const uint64_t first = n_chunks == 1 ? 0 : c0 * L.channel_len;
+    const uint64_t count = n_chunks == 1 ? total : (c1 - c0) * L.channel_len;
+    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
+    rc = decode_pipeline(c, FRONT_DEGA, d_payload, d_bits + s0, d_boff + s0, Lk, max_len, params, d_samples + first, d_nout + s0,
+                         d_status + s0);
+    if (rc != DC_OK)
+      return rc;
+    CU_TRY(c, cudaEventRecord(c->ev_out[k], c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaStreamWaitEvent(c->s_d2h, c->ev_out[k], 0), DC_ERR_LIBRARY_CALL);
+    if (samples && count)
+      CU_TRY(c, cudaMemcpyAsync(samples + first, d_samples + first, count * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    if (n_out && s1 > s0)
+      CU_TRY(c, cudaMemcpyAsync(n_out + s0, d_nout + s0, (s1 - s0) * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+    if (status && s1 > s0)
+      CU_TRY(c, cudaMemcpyAsync(status + s0, d_status + s0, (s1 - s0) * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
   CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)

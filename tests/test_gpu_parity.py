@@ -169,6 +169,24 @@ def test_host_buffer_face(ctx, oracle):
     assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not status.any()
 
 
+def test_host_buffer_face_chunked_overlap(ctx, oracle):
+    """Enough streams for the host-buffer calls to split into overlapped channel chunks (>= 2 waves of coder CTAs)."""
+    from data_compressor_b200 import synth
+    nc, cl, bl = 1301, 4000, 16            # 325,250 streams -> 2 chunks of 651/650 channels
+    x = synth.redd_like(nc, cl, device="cpu", seed=77).numpy()
+    payload, bit_len, byte_off, status = ctx.dega_encode_host(x, block_len=bl)
+    assert not status.any() and int(byte_off[-1]) == payload.size
+    assert np.array_equal(byte_off[1:] - byte_off[:-1], (bit_len + 7) // 8)
+    rng = np.random.default_rng(1)
+    for s in list(rng.integers(0, bit_len.size, 12)) + [0, 651 * 250 - 1, 651 * 250, bit_len.size - 1]:
+        c, b = divmod(int(s), 250)
+        want = oracle.dega_encode(x[c, b * bl:(b + 1) * bl])[1]
+        o = int(byte_off[s])
+        assert payload[o:o + len(want)].tobytes() == want, s
+    y, n_out, st2 = ctx.dega_decode_host(payload, bit_len, byte_off, nc, cl, bl)
+    assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not st2.any() and (n_out == bl).all()
+
+
 def test_axdr_normalize_only(ctx, oracle):
     rng = np.random.default_rng(5)
     x = profile(rng, (50, 96), step=40, base=500)
