@@ -228,7 +228,11 @@ def run_ours(args):
     ctx.set_profiling(True)
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 5.0:   # nvidia-smi start-up stalls the driver: keep it out of the timed region
+        time.sleep(0.05)
+    for _ in range(2):
+        step()
     barrier()
     launches0 = ctx.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
@@ -421,7 +425,7 @@ def run_secondary(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS)
