@@ -39,51 +39,53 @@ def workload_name(channels, samples, block_len):
 
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed region through NVML (in-process: the nvidia-smi CLI in
+    loop mode stalls the driver for milliseconds per sample, which showed up as 5-10 ms of extra step time)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.05):
         super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.period = period
         self.rows = []
         self.stop_flag = False
-        self.proc = None
+        self.max_mhz = None
+        self.ok = False
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.ok = True
+            while not self.stop_flag:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, reasons))
+                time.sleep(self.period)
+        except Exception as ex:   # no NVML: report it, never fail the bench
+            self.rows.append((None, repr(ex)))
 
     def stop(self):
         self.stop_flag = True
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
+        sm = [r[0] for r in self.rows if r[0] is not None]
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": str(self.rows[-1][1]) if self.rows else "no samples"}
+        bits = 0
+        for r in self.rows:
+            if r[0] is not None:
+                bits |= r[1]
+        # NVML clocks-event-reason bits (nvml.h): 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(v for k, v in names.items() if bits & k),
+                "samples": len(sm), "how": "NVML, 50 ms period, during the timed region"}
 
 
 def measured_peak():
@@ -227,9 +229,10 @@ def run_ours(args):
         step()
     ctx.set_profiling(True)
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("DC_BENCH_NO_CLOCKS"):
+        sampler.start()
     t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 5.0:   # nvidia-smi start-up stalls the driver: keep it out of the timed region
+    while sampler.is_alive() and not sampler.rows and time.time() - t_wait < 5.0:   # NVML initialisation stays out of the timed region
         time.sleep(0.05)
     for _ in range(2):
         step()
@@ -237,11 +240,13 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kernel_ms = {}
     t_enc = t_dec = 0.0
     with torch.cuda.stream(ctx.stream):
         ev0.record(ctx.stream)
-        for _ in range(args.steps):
+        step_ev[0].record(ctx.stream)
+        for it in range(args.steps):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
             if world > 1:
@@ -250,10 +255,12 @@ def run_ours(args):
             km2 = ctx.kernel_ms()
             for k, v in list(km.items()) + list(km2.items()):
                 kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+            step_ev[it + 1].record(ctx.stream)
         ev1.record(ctx.stream)
     barrier()
     launches = ctx.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
+    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     sampler.stop()
     ctx.set_profiling(False)
     ok = bool(torch.equal(y.view(torch.int32), x.view(torch.int32))) and not bool(enc.status.any().item())
@@ -336,7 +343,7 @@ def run_ours(args):
         "compression_ratio": world * raw_bytes / float(tot_bytes.item()),
         "encode_ms": sum(kernel_ms.get(k, 0.0) for k in ("front", "bac_encode", "scan", "gather")),
         "decode_ms": sum(kernel_ms.get(k, 0.0) for k in ("bac_decode", "back")),
-        "kernel_ms": kernel_ms, "round_trip_ok": ok,
+        "kernel_ms": kernel_ms, "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)], "round_trip_ok": ok,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

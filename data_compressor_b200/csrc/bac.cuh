@@ -109,6 +109,10 @@ struct BacModel
 //
 // Pipe balance: ncu shows this kernel bound by the integer ALU pipe (shifts, logic, compares) with the FMA pipe (IMAD)
 // two-thirds idle, so variable shifts are done as multiplications by 2^n wherever the product is needed anyway.
+// MUL_SHIFT picks how the final `<< n` of (rng, LO) is done: as multiplications by 2^n (FMA pipe) or as shifts (ALU pipe).
+// The encoder is FMA-heavy elsewhere and takes shifts; the decoder is ALU-heavy elsewhere and takes multiplications
+// (profiles/r1d_dega_ncu_summary.txt: both pipes end up near 70 %).
+template <bool MUL_SHIFT>
 __device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3, uint32_t &P1)
 {
   const uint32_t HI = LO0 + (r1 << 16) - 1;   // (hi << 16) | 0xFFFF
@@ -116,9 +120,18 @@ __device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &
   P1 = shl_c(1u, n1);                         // opaque to the optimiser: keeps the multiplications below
   const uint32_t z = ~LO0 | HI;               // clear exactly where lo has 1 and hi has 0
   n3 = clz_nz((z * P1) << 1);                 // run below the first differing bit, capped by the guard ones
-  const uint32_t Pn = shl_c(P1, n3);          // n1 + n3 <= 31
-  rng = r1 * Pn;
-  LO = (LO0 * Pn) & 0x7FFF0000u;
+  if (MUL_SHIFT)
+  {
+    const uint32_t Pn = shl_c(P1, n3);        // n1 + n3 <= 31
+    rng = r1 * Pn;
+    LO = (LO0 * Pn) & 0x7FFF0000u;
+  }
+  else
+  {
+    const uint32_t n = n1 + n3;               // <= 31
+    rng = r1 << n;
+    LO = (LO0 << n) & 0x7FFF0000u;
+  }
 }
 
 struct BacEncoder
@@ -140,7 +153,7 @@ struct BacEncoder
   __device__ __forceinline__ void renorm_emit(uint32_t LO0, uint32_t r1, BitWriter &w)
   {
     uint32_t n1, n3, P1;
-    bac_renorm(LO0, r1, LO, rng, n1, n3, P1);
+    bac_renorm<false>(LO0, r1, LO, rng, n1, n3, P1);
     const bool some = n1 != 0;
     const uint32_t k = some ? n1 + pend : 0u;   // bits leaving now: n1 plus the pending run spliced after the first
     const uint32_t p0 = pend;
@@ -162,8 +175,8 @@ struct BacEncoder
       return;
     }
     // top n1 bits of lo, with the pending run spliced in: bits + 2^(k-1) - 2^(n1-1); k <= 31 here
-    const uint32_t Pk = shl_c(1u, k);
-    w.acc = w.acc * Pk + (__umulhi(LO0, P1) + ((Pk - P1) >> 1));
+    const uint32_t Pk = 1u << k;
+    w.acc = (w.acc << k) | (uint64_t)(__umulhi(LO0, P1) + ((Pk - P1) >> 1));
     w.nacc += k;
   }
 

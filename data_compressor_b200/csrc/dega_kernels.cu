@@ -21,7 +21,11 @@ __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
     front_body(a, s);
 }
 
-__global__ void __launch_bounds__(128) front_dega_kernel(const FrontArgs a)
+#ifndef FRONT_MIN_CTAS
+#define FRONT_MIN_CTAS 12
+#endif
+// CTAs of 128 threads; FRONT_MIN_CTAS bounds the register count (16 -> 32 registers would spill the prefetch buffers)
+__global__ void __launch_bounds__(128, FRONT_MIN_CTAS) front_dega_kernel(const FrontArgs a)
 {
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < a.lay.n_streams)
@@ -49,11 +53,12 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
     back_body(a, s);
 }
 
-__global__ void __launch_bounds__(128) back_dega_kernel(const BackArgs a)
+__global__ void __launch_bounds__(128, 16) back_dega_kernel(const BackArgs a)
 {
+  __shared__ float stage[128 * 4];   // four decoded samples per thread, leaving as one 128-bit store
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < a.n_streams)
-    back_dega_body(a, s);
+    back_dega_body(a, s, stage + threadIdx.x * 4);
 }
 
 void launch_back(const BackArgs &a, cudaStream_t st)
@@ -62,7 +67,9 @@ void launch_back(const BackArgs &a, cudaStream_t st)
     return;
   const unsigned block = 128;
   const unsigned grid = (unsigned)((a.n_streams + block - 1) / block);
-  if (a.in_seg && a.do_undiff && a.do_denorm && a.vs >= 17)
+  // the specialised kernel reads the 4-byte aligned SEG scratch (fixed stride); anything else takes the general one
+  if (a.in_seg && a.do_undiff && a.do_denorm && a.vs >= 17 && a.in.byte_off == nullptr && (a.in.stride_bytes & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.in.base) & 3) == 0)
     back_dega_kernel<<<grid, block, 0, st>>>(a);
   else
     back_kernel<<<grid, block, 0, st>>>(a);

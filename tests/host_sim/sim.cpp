@@ -192,7 +192,10 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       ka.n_out = &meta[3];
       ka.status = status;
       if (ka.in_seg && ka.do_undiff && ka.do_denorm && ka.vs >= 17)
-        back_dega_body(ka, 0);
+      {
+        float stage4[4];
+        back_dega_body(ka, 0, stage4);
+      }
       else
         back_body(ka, 0);
     }
@@ -343,7 +346,10 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
     else
       bac_decode_body<false>(ba, s, div_table());
     if (vs >= 17)
-      back_dega_body(ka, s);
+    {
+      float stage4[4];
+      back_dega_body(ka, s, stage4);
+    }
     else
       back_body(ka, s);
   }
