@@ -14,8 +14,8 @@
 //   update    index 1: hi unchanged, lo += A                    A = floor(rng * c1 / total)
 //             index 2: lo += B, rng = A - B                      B = floor(rng / total)
 //             EOF    : rng = B                                    (bac.c:109-111 with the cum[] above)
-//   division  total <= 16383 and rng * c1 <= 2^29, so floor(x / total) == umulhi(x << 2, m) >> l with a
-//             precomputed round-up reciprocal (m, l) per divisor (kernels.h: DivEntry); exact, no correction step.
+//   division  total <= 16383 and rng * c1 <= 2^29, so floor(x / total) == umulhi(x, m) >> s with a
+//             precomputed round-up reciprocal (m, s) per divisor (kernels.h: DivEntry); exact, no correction step.
 //   renorm    bac.c:112-137 is a loop of three cases.  Closed form: first n1 = number of equal leading bits of
 //             (lo, hi) "E1/E2" steps, each emitting that bit; then n3 = length of the run "lo = 01..., hi = 10..."
 //             below the top bit, each an "E3" step (pending++).  After an E3 step lo < 0x8000 <= hi, so no E1/E2
@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t clz_nz(uint32_t a)
 #endif
 
 // floor(x / d) for x < 2^30 with the table entry of d
-__device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x << 2, e.m) >> e.l; }
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x, e.m) >> e.s; }
 
 struct BacModel
 {

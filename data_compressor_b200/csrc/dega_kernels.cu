@@ -505,19 +505,4 @@ void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t
   g_launches++;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-void build_div_table(DivEntry *t)
-{
-  t[0].m = 0;
-  t[0].l = 0;
-  for (uint32_t d = 1; d < (uint32_t)kDivTableEntries; d++)
-  {
-    uint32_t l = 0;
-    while ((1u << l) < d)
-      l++;
-    t[d].m = (uint32_t)((((uint64_t)1 << (30 + l)) + d - 1) / d);
-    t[d].l = l;
-  }
-}
-
 }  // namespace dc

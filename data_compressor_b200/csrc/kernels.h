@@ -35,15 +35,31 @@ __host__ __device__ inline void stream_extent(const Layout &L, uint64_t s, uint6
   }
 }
 
-// Division table for the arithmetic coder: entry d = {m, l} with floor(x / d) == umulhi(x << 2, m) >> l for
-// every x < 2^30 (exact, Granlund-Montgomery round-up).  16384 entries, entries 0..1 unused.
+// Division table for the arithmetic coder: for 3 <= d < 16384, entry d = {m, s} with
+//   floor(x / d) == umulhi(x, m) >> s          for every x < 2^30
+// (exact Granlund-Montgomery round-up reciprocal: l = ceil(log2 d), m = ceil(2^(30+l) / d) < 2^31, s = l - 2).
+// Entries 0..2 are unused (the coder's total frequency is at least 3).
 struct DivEntry
 {
   uint32_t m;
-  uint32_t l;
+  uint32_t s;
 };
 static const int kDivTableEntries = 16384;
-void build_div_table(DivEntry *host_table);
+inline void build_div_table(DivEntry *t)
+{
+  for (uint32_t d = 0; d < (uint32_t)kDivTableEntries; d++)
+  {
+    t[d].m = 0;
+    t[d].s = 0;
+    if (d < 3)
+      continue;
+    uint32_t l = 0;
+    while ((1u << l) < d)
+      l++;
+    t[d].m = (uint32_t)((((uint64_t)1 << (30 + l)) + d - 1) / d);
+    t[d].s = l - 2;
+  }
+}
 
 // ---- front end: [normalize] -> [diff] -> {seg | fixed-width pack} ---------------------------------
 struct FrontArgs
