@@ -2,28 +2,38 @@
 //
 // The reference is the Witten/Neal/Cleary coder with RANGE_BITS = 16 over the three symbols {0, 1, EOF}
 // (bac.c:13,29-31).  This restatement keeps the same integer results but re-expresses the state so that one
-// symbol costs a fixed, branch-free instruction sequence per thread (the kernel is integer-issue bound):
+// symbol costs a short, branch-free instruction sequence per thread (the kernels are integer-issue bound):
 //
-//   state     reference keeps (start_range, end_range) (bac.c:83); we keep (LO, rng): LO = start_range << 16
-//             (top-aligned in a 32-bit register) and rng = end - start + 1, because every renormalisation step
-//             doubles rng whatever branch it takes.
+//   state     reference keeps (start_range, end_range, next_bits) (bac.c:83-84).  We keep (LO, rng):
+//             rng = end - start + 1 (every renormalisation step doubles it whatever branch it takes) and LO = the
+//             TRUE low end of the interval, top-aligned in a 32-bit register (bits 31..16, low half zero), i.e. the
+//             16-bit window of the exact, arbitrarily long binary fraction that the coder is narrowing down.
+//   pending   the reference never lets a carry reach bits it has already written: in the "E3" case
+//             (lo = 01.., hi = 10..) it subtracts 0x4000, counts a pending bit and later writes the run inverted
+//             (bac.c:93-105,124-129).  In the exact-fraction view that is nothing but carry propagation: while
+//             bits are pending, the true window is the reference's window with the top bit flipped
+//             (lo_true = lo ^ 0x8000, same for hi), the bits that left the window are 0 1 1 1 ..., and the
+//             reference's "lo >= 0x8000 -> write 1 then zeros" is the carry rippling through that run.  So here the
+//             window simply overflows into the bits shifted out before (a0 / the CarryWriter accumulator, and --
+//             about once in 2^32 flushes -- into words already stored, which are private to the thread).  Output
+//             bits are identical to the reference's; there is no pending counter and no splice on the hot path.
+//   counts    the number of doublings per symbol is the reference's: n1 = number of equal leading bits of
+//             (lo, hi) "E1/E2" steps, then n3 = length of the run "lo = .1.., hi = .0.." below the first differing bit
+//             "E3" steps (after an E3 step lo < 0x8000 <= hi, so no E1/E2 step can follow within the same symbol).
+//             Both windows carry the same flipped top bit while bits are pending, so lo ^ hi and the bits below the
+//             top are the same in both views: one CLZ each, with HI = (hi << 16) | 0xFFFF capping them (lo == hi).
 //   model     the reference keeps freq[4]/cum[4]/two index maps (bac.c:33-37).  EOF never moves and keeps
 //             frequency 1 (UpdateModel is never called with index 3; halving maps 1 -> 1, bac.c:63) and index 0 is
-//             a sentinel, so the whole adaptive model is (f_top, c1 = f_oth + 1, topmask, total): the counts of
-//             the data symbols at index 1 / 2 and which bit sits at index 1.  cum[] = {total, c1, 1, 0}.
-//   update    index 1: hi unchanged, lo += A                    A = floor(rng * c1 / total)
-//             index 2: lo += B, rng = A - B                      B = floor(rng / total)
+//             a sentinel, so the whole adaptive model is (f_top, f_oth, top): the counts of the data symbols at
+//             index 1 / 2 and which bit sits at index 1.  cum[] = {f_top + f_oth + 1, f_oth + 1, 1, 0}.
+//   update    index 1: hi unchanged, lo += A                    A = floor(rng * cum[1] / cum[0])
+//             index 2: lo += B, rng = A - B                      B = floor(rng / cum[0])
 //             EOF    : rng = B                                    (bac.c:109-111 with the cum[] above)
-//   division  total <= 16383 and rng * c1 <= 2^29, so floor(x / total) == umulhi(x, m) >> s with a
+//   division  total <= 16383 and rng * cum[1] <= 2^30, so floor(x / total) == umulhi(x, m) >> s with a
 //             precomputed round-up reciprocal (m, s) per divisor (kernels.h: DivEntry); exact, no correction step.
-//   renorm    bac.c:112-137 is a loop of three cases.  Closed form: first n1 = number of equal leading bits of
-//             (lo, hi) "E1/E2" steps, each emitting that bit; then n3 = length of the run "lo = 01..., hi = 10..."
-//             below the top bit, each an "E3" step (pending++).  After an E3 step lo < 0x8000 <= hi, so no E1/E2
-//             step can follow within the same symbol.  With HI = (hi << 16) | 0xFFFF both counts are one CLZ each
-//             and the low ones of HI cap them without a special case for lo == hi.
-//   emission  OutputNextBits (bac.c:93-105) writes a bit followed by `pending` inverted bits.  For n1 >= 1 E1/E2
-//             steps the output is the top n1 bits of lo with the pending run spliced in after the first one, i.e.
-//             the (n1 + pending)-bit number  bits + 2^(n1+pending-1) - 2^(n1-1)  -- one append, no loop.
+//   end       EOF symbol, then FinishEncoding (bac.c:141-145): one more pending bit, then the bit
+//             (lo < 0x4000 ? 0 : 1) followed by the inverted run -- in the exact view: add 0x4000 to the window
+//             (with carry) and shift two more bits out.
 #pragma once
 
 #include <stdint.h>
@@ -66,139 +76,303 @@ __device__ __forceinline__ uint32_t clz_nz(uint32_t a)
 }
 #endif
 
-// floor(x / d) for x < 2^30 with the table entry of d
+// floor(x / d) for x <= 2^30 with the table entry of d
 __device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x, e.m) >> e.s; }
 
 struct BacModel
 {
-  uint32_t f_top;     // freq[1]
-  uint32_t topmask;   // index_to_symbol[1] as 0 / 0x80000000
-  uint32_t total;     // cum[0] = freq[1] + freq[2] + 1, so cum[1] = freq[2] + 1 = total - f_top
+  uint32_t f_top;   // freq[1]
+  uint32_t f_oth;   // freq[2]; cum[1] = f_oth + 1, cum[0] = f_top + f_oth + 1
+  uint32_t top;     // index_to_symbol[1] as 0 / 0xFFFFFFFF
 
   __device__ __forceinline__ void init()   // InitModel, bac.c:39-52
   {
     f_top = 1;
-    topmask = 0;
-    total = 3;
+    f_oth = 1;
+    top = 0;
   }
 
-  __device__ __forceinline__ uint32_t c1() const { return total - f_top; }   // cum[1]
+  __device__ __forceinline__ uint32_t total() const { return f_top + f_oth + 1; }   // cum[0]
 
-  // bac.c:57-67: halve, rounding up; EOF stays at 1.  Only when total == kBacMaxFreq.
+  // bac.c:57-67: halve, rounding up; EOF stays at 1.  Only when total() == kBacMaxFreq.
   __device__ __forceinline__ void halve()
   {
-    const uint32_t f_oth = (total - f_top) >> 1;   // ((freq[2]) + 1) / 2 with freq[2] = total - f_top - 1
     f_top = (f_top + 1) >> 1;
-    total = f_top + f_oth + 1;
+    f_oth = (f_oth + 1) >> 1;
   }
 
-  // UpdateModel, bac.c:68-80, for a data symbol; bm = the coded bit as 0 / 0x80000000, is_top == (bm == topmask)
-  __device__ __forceinline__ void bump(uint32_t bm, bool is_top)
+  // UpdateModel, bac.c:68-80, for a data symbol that sat at index 1 (is_top) or 2.  Returns true when the two data
+  // symbols traded places (bac.c:68-77: a symbol at index 2 moves left past its equal-frequency neighbour,
+  // freq[2] == freq[1], and then counts as freq[1]).  That is rare on skewed data, so it is the only branch; the
+  // common case is one predicated increment.
+  __device__ __forceinline__ bool bump(bool is_top)
   {
-    // bac.c:68: a symbol at index 2 moves left past its equal-frequency neighbour (freq[2] == freq[1], i.e.
-    // total == 2 * freq[1] + 1), then freq[1]++; otherwise freq[2]++ (implied by total++)
-    const bool inc_top = is_top || (total == 2 * f_top + 1);
-    topmask = inc_top ? bm : topmask;     // is_top: bm == topmask already; tie: the coded symbol takes index 1
-    f_top += inc_top ? 1u : 0u;
-    total++;
+    if (!is_top && f_oth == f_top)
+    {
+      top = ~top;
+      f_top++;
+      return true;
+    }
+    if (is_top)
+      f_top++;
+    else
+      f_oth++;
+    return false;
   }
 };
 
-// Interval after coding a symbol: LO0 (top-aligned lo), r1 (range).  Returns the E1/E2 count n1, the E3 count n3 and
-// P1 = 2^n1, and leaves the renormalised interval in (LO, rng).  bac.c:112-137.
-//
-// Pipe balance: ncu shows this kernel bound by the integer ALU pipe (shifts, logic, compares) with the FMA pipe (IMAD)
-// two-thirds idle, so variable shifts are done as multiplications by 2^n wherever the product is needed anyway.
-// MUL_SHIFT picks how the final `<< n` of (rng, LO) is done: as multiplications by 2^n (FMA pipe) or as shifts (ALU pipe).
-// The encoder is FMA-heavy elsewhere and takes shifts; the decoder is ALU-heavy elsewhere and takes multiplications
-// (profiles/r1d_dega_ncu_summary.txt: both pipes end up near 70 %).
-template <bool MUL_SHIFT>
-__device__ __forceinline__ void bac_renorm(uint32_t LO0, uint32_t r1, uint32_t &LO, uint32_t &rng, uint32_t &n1, uint32_t &n3, uint32_t &P1)
+// ---------------------------------------------------------------------------------------------------
+// Hot-path form of "which symbol, its sub-interval, UpdateModel" for the unrolled symbol groups (no halving inside).
+// Written as predicated PTX because the compiler's own if-conversion of the C++ above costs three times as many
+// instructions; results are those of BacModel::bump.  In: A, B (see "update" at the top), rng, and
+//   encoder: x = input word ^ top, mask = the symbol's bit; a set bit means the symbol sits at index 2.  When the
+//            symbols trade places x is inverted, so it stays "word ^ top".
+//   decoder: o = value - lo; the symbol sits at index 2 when o < A.  nontop collects those bits, inv collects `top`
+//            for every position of the group (it changes for all later positions when the symbols trade places).
+// Out: dlo = what is added to lo, base - dlo = the new range.
+template <bool ADAPTIVE>
+__device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_t A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &dlo,
+                                             uint32_t &base)
 {
-  const uint32_t HI = LO0 + (r1 << 16) - 1;   // (hi << 16) | 0xFFFF
-  n1 = clz_nz(LO0 ^ HI);                      // 0..16 (the low 16 bits of the xor are ones)
-  P1 = shl_c(1u, n1);                         // opaque to the optimiser: keeps the multiplications below
-  const uint32_t z = ~LO0 | HI;               // clear exactly where lo has 1 and hi has 0
-  n3 = clz_nz((z * P1) << 1);                 // run below the first differing bit, capped by the guard ones
-  if (MUL_SHIFT)
-  {
-    const uint32_t Pn = shl_c(P1, n3);        // n1 + n3 <= 31
-    rng = r1 * Pn;
-    LO = (LO0 * Pn) & 0x7FFF0000u;
-  }
+#ifdef DC_HOST_SIM
+  const bool is_top = (x & mask) == 0;
+  dlo = is_top ? A : B;
+  base = is_top ? rng : A;
+  const uint32_t top0 = m.top;   // the caller derives `top` from x at the end of the group
+  if (ADAPTIVE && m.bump(is_top))
+    x = ~x;
+  m.top = top0;
+#else
+  if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn, ps, pi;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %4, %5;\n\t"
+        "setp.ne.u32 pn, t, 0;\n\t"
+        "selp.u32 %0, %7, %6, pn;\n\t"
+        "selp.u32 %1, %6, %8, pn;\n\t"
+        "setp.eq.and.u32 ps, %3, %2, pn;\n\t"
+        "@ps not.b32 %4, %4;\n\t"
+        "not.pred pi, pn;\n\t"
+        "or.pred pi, pi, ps;\n\t"
+        "@pi add.u32 %2, %2, 1;\n\t"
+        "@!pi add.u32 %3, %3, 1;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base), "+r"(m.f_top), "+r"(m.f_oth), "+r"(x)
+        : "r"(mask), "r"(A), "r"(B), "r"(rng));
   else
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 pn, t, 0;\n\t"
+        "selp.u32 %0, %5, %4, pn;\n\t"
+        "selp.u32 %1, %4, %6, pn;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base)
+        : "r"(x), "r"(mask), "r"(A), "r"(B), "r"(rng));
+#endif
+}
+
+template <bool ADAPTIVE>
+__device__ __forceinline__ void bac_pick_dec(uint32_t o, uint32_t bit, uint32_t A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &nontop,
+                                             uint32_t &inv, uint32_t &dlo, uint32_t &base)
+{
+#ifdef DC_HOST_SIM
+  const bool is_top = o >= A;
+  dlo = is_top ? A : B;
+  base = is_top ? rng : A;
+  if (!is_top)
+    nontop |= bit;
+  const uint32_t top0 = m.top;   // the caller derives `top` from inv at the end of the group
+  if (ADAPTIVE && m.bump(is_top))
+    inv ^= bit - 1;
+  m.top = top0;
+#else
+  if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn, ps, pi;\n\t"
+        "setp.lt.u32 pn, %6, %8;\n\t"
+        "selp.u32 %0, %9, %8, pn;\n\t"
+        "selp.u32 %1, %8, %10, pn;\n\t"
+        "@pn or.b32 %4, %4, %7;\n\t"
+        "setp.eq.and.u32 ps, %3, %2, pn;\n\t"
+        "@ps xor.b32 %5, %5, %11;\n\t"
+        "not.pred pi, pn;\n\t"
+        "or.pred pi, pi, ps;\n\t"
+        "@pi add.u32 %2, %2, 1;\n\t"
+        "@!pi add.u32 %3, %3, 1;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base), "+r"(m.f_top), "+r"(m.f_oth), "+r"(nontop), "+r"(inv)
+        : "r"(o), "r"(bit), "r"(A), "r"(B), "r"(rng), "r"(bit - 1));
+  else
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        "setp.lt.u32 pn, %3, %5;\n\t"
+        "selp.u32 %0, %6, %5, pn;\n\t"
+        "selp.u32 %1, %5, %7, pn;\n\t"
+        "@pn or.b32 %2, %2, %4;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base), "+r"(nontop)
+        : "r"(o), "r"(bit), "r"(A), "r"(B), "r"(rng));
+#endif
+}
+
+// Number of doublings (bac.c:112-137) of the interval (LO0, r1): LO0 = top-aligned low end, r1 = range.
+__device__ __forceinline__ uint32_t bac_doublings(uint32_t LO0, uint32_t r1)
+{
+  const uint32_t HI = LO0 + (r1 << 16) - 1;          // (hi << 16) | 0xFFFF; may wrap while bits are pending
+  const uint32_t n1 = clz_nz(LO0 ^ HI);              // 0..16 (the low 16 bits of the xor are ones)
+  const uint32_t z = ~LO0 | HI;                      // clear exactly where lo has 1 and hi has 0
+  const uint32_t y = z << n1;
+  const uint32_t n3 = clz_nz(y + y);                 // run below the first differing bit, capped by the guard ones
+  return n1 + n3;                                    // <= 16
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Output of the encoder: MSB-first bit stream whose tail can still take a carry.
+//   acc   low nacc bits = bits not yet stored; bit nacc (at most one, see below) = a carry that still has to be
+//         added to what was stored before; nothing above.
+// The interval only ever shrinks, so the bits in front of any position change at most once (by +1) after they were
+// produced: one carry bit per flush is all there is, and the ripple into stored words stops at the first word that
+// does not wrap.
+// +1 on the big-endian number formed by the stored words (rare: the tail of the stored bits was all ones).
+// Out of line and by value so that the writer's state never has to live in local memory.
+__device__ __noinline__ static void bac_ripple(uint32_t *words, uint32_t nwords)
+{
+  for (uint32_t i = nwords; i-- > 0;)
   {
-    const uint32_t n = n1 + n3;               // <= 31
-    rng = r1 << n;
-    LO = (LO0 << n) & 0x7FFF0000u;
+    const uint32_t v = bswap32(words[i]) + 1u;
+    words[i] = bswap32(v);
+    if (v != 0)
+      break;
   }
 }
 
+struct CarryWriter
+{
+  uint32_t *words;
+  uint32_t cap_words;
+  uint32_t nwords;
+  uint32_t nacc;      // < 32 between calls
+  uint64_t acc;
+  bool overflow;      // valid after finish()
+
+  __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes)
+  {
+    words = reinterpret_cast<uint32_t *>(p);
+    cap_words = (uint32_t)(cap_bytes >> 2);
+    nwords = 0;
+    nacc = 0;
+    acc = 0;
+    overflow = false;
+  }
+
+  __device__ __forceinline__ void ripple()
+  {
+    if (nwords <= cap_words)   // else the stream has outgrown its region: it is reported as overflow and redone
+      bac_ripple(words, nwords);
+  }
+
+  __device__ __forceinline__ void flush_word()   // requires 32 <= nacc <= 63
+  {
+    const uint32_t k = nacc - 32;
+    const uint64_t t = acc >> k;                 // 32 bits to store + the carry bit
+    acc &= ~(~0ull << k);
+    nacc = k;
+    if ((uint32_t)(t >> 32))
+      ripple();
+    if (nwords < cap_words)
+      words[nwords] = bswap32((uint32_t)t);
+    nwords++;
+  }
+
+  // appends the low k bits of v (k <= 31); bit k of v, if set, is a carry into the bits appended earlier
+  __device__ __forceinline__ void push(uint32_t v, uint32_t k)
+  {
+    acc = (acc << k) + v;
+    nacc += k;
+    if (nacc >= 32)
+      flush_word();
+  }
+
+  __device__ __forceinline__ uint64_t bits() const { return (uint64_t)nwords * 32 + nacc; }
+
+  // resolves a carry that is still waiting, stores the fractional word (left aligned, zero padded)
+  __device__ __forceinline__ uint64_t finish()
+  {
+    if ((uint32_t)(acc >> nacc))
+    {
+      ripple();
+      acc &= ~(~0ull << nacc);
+    }
+    const uint64_t total = bits();
+    overflow = nwords + (nacc ? 1u : 0u) > cap_words;
+    if (nacc && nwords < cap_words)
+      words[nwords] = bswap32((uint32_t)acc << (32 - nacc));
+    return total;
+  }
+};
+
 struct BacEncoder
 {
-  uint32_t LO;      // start_range << 16
-  uint32_t rng;     // end_range - start_range + 1, in [1, 65536]
-  uint32_t pend;    // next_bits, bac.c:84
+  uint32_t LO;    // true low end << 16
+  uint32_t rng;   // end_range - start_range + 1, in [1, 65536]
+  uint32_t a0;    // bits that left LO since the last drain: low kg bits, plus a carry at bit kg
+  uint32_t kg;    // <= 31
 
   __device__ __forceinline__ void init()   // StartEncoding, bac.c:86-91
   {
     LO = 0;
     rng = 0x10000u;
-    pend = 0;
+    a0 = 0;
+    kg = 0;
   }
 
-  // renormalise (LO0, r1) and emit (bac.c:112-137 + OutputNextBits, bac.c:93-105).
-  // The writer's 64-bit accumulator may hold up to 64 bits here; the CALLER drains it (w.drain()) every few symbols,
-  // at a warp-uniform point, so that the data-dependent "word is full" branch is not taken per symbol.
-  __device__ __forceinline__ void renorm_emit(uint32_t LO0, uint32_t r1, BitWriter &w)
+  // hands the group's bits to the writer; called at warp-uniform points (every 8 symbols) and whenever a symbol
+  // would push kg past 31 (rare: a load profile yields < 1 bit per symbol and at most 4 per symbol in practice)
+  __device__ __forceinline__ void drain(CarryWriter &w)
   {
-    uint32_t n1, n3, P1;
-    bac_renorm<false>(LO0, r1, LO, rng, n1, n3, P1);
-    const bool some = n1 != 0;
-    const uint32_t k = some ? n1 + pend : 0u;   // bits leaving now: n1 plus the pending run spliced after the first
-    const uint32_t p0 = pend;
-    pend = (some ? 0u : pend) + n3;
-    // One rare region per symbol: k >= 32 (more than 16 consecutive E3 steps) or the accumulator would overflow
-    // (nacc + k > 64 with k < 32 implies k + nacc/2 > 33).
-    if (k + (w.nacc >> 1) >= 32)
-    {
-      w.drain();
-      if (k > 32)
-      {
-        const uint32_t first = LO0 >> 31;
-        w.put(first, 1);
-        w.run(first ^ 1u, p0);
-        w.put(shr_c(LO0 << 1, 33 - n1), n1 - 1);
-      }
-      else
-        w.put(shr_c(LO0, 32 - n1) + shl_c(1u, k - 1) - shl_c(1u, n1 - 1), k);
-      return;
-    }
-    // top n1 bits of lo, with the pending run spliced in: bits + 2^(k-1) - 2^(n1-1); k <= 31 here
-    const uint32_t Pk = 1u << k;
-    w.acc = (w.acc << k) | (uint64_t)(__umulhi(LO0, P1) + ((Pk - P1) >> 1));
-    w.nacc += k;
+    w.push(a0, kg);
+    a0 = 0;
+    kg = 0;
   }
 
-  // EncodeSymbol for a data bit (bac.c:107-111)
-  __device__ __forceinline__ void encode_bit(bool is_top, uint32_t c1, const DivEntry e, BitWriter &w)
+  // interval update lo += dlo, range = r1 (bac.c:109-111), renormalisation and output (bac.c:112-137)
+  __device__ __forceinline__ void narrow(uint32_t dlo, uint32_t r1, CarryWriter &w)
   {
-    const uint32_t A = div_magic(rng * c1, e);
+    const uint64_t x = (((uint64_t)a0 << 32) | LO) + ((uint64_t)dlo << 16);   // the window overflows into a0
+    const uint32_t LO0 = (uint32_t)x;
+    a0 = (uint32_t)(x >> 32);
+    const uint32_t n = bac_doublings(LO0, r1);
+    if (kg + n > 31)
+      drain(w);
+    kg += n;
+    rng = r1 << n;
+    a0 = __funnelshift_l(LO0, a0, n);
+    LO = LO0 << n;
+  }
+
+  // EncodeSymbol for a data bit (bac.c:107-111); c1 = cum[1]
+  __device__ __forceinline__ void encode_bit(bool is_top, uint32_t c1m1, const DivEntry e, CarryWriter &w)
+  {
+    const uint32_t A = div_magic(rng * c1m1 + rng, e);
     const uint32_t B = div_magic(rng, e);
     const uint32_t dlo = is_top ? A : B;
     const uint32_t base = is_top ? rng : A;
-    renorm_emit(LO + (dlo << 16), base - dlo, w);
+    narrow(dlo, base - dlo, w);
   }
 
   // EOF symbol (bac.c:163) followed by FinishEncoding (bac.c:141-145)
-  __device__ __forceinline__ void finish(const DivEntry e, BitWriter &w)
+  __device__ __forceinline__ void finish(const DivEntry e, CarryWriter &w)
   {
-    renorm_emit(LO, div_magic(rng, e), w);
-    w.drain();
-    const uint32_t bit = LO < 0x40000000u ? 0u : 1u;
-    w.put(bit, 1);
-    w.run(bit ^ 1u, (uint64_t)pend + 1);
-    pend = 0;
+    narrow(0, div_magic(rng, e), w);
+    drain(w);
+    const uint64_t x = (((uint64_t)a0 << 32) | LO) + 0x40000000ull;
+    a0 = (uint32_t)(x >> 32);
+    a0 = (a0 << 2) | ((uint32_t)x >> 30);
+    kg = 2;
+    drain(w);
   }
 };
 

@@ -161,3 +161,80 @@ def split_streams(x, block_len):
         for b in range(0, max(cl, 1), bl):
             out.append(x[c, b:b + bl])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def straddling_bits(n_straddle, tail, adaptive=1, prefix=(), resolve=None):
+    """Input bits for the arithmetic coder that keep the coding interval straddling the midpoint for `n_straddle`
+    symbols (pure-Python model of bac.c:54-81,107-137): every such symbol adds pending bits (E3 steps), i.e. a
+    long run of output bits that a later symbol resolves with or without a carry.  resolve="up"/"down" appends the
+    symbol that puts the whole interval above/below the midpoint (a carry into the run / none); `tail` follows."""
+    freq, cum = [0, 1, 1, 1], [3, 2, 1, 0]
+    s2i, i2s = [1, 2], [0, 0, 1, 0]
+    lo, hi = 0, 0xFFFF
+    out = []
+
+    def code(bit):
+        nonlocal lo, hi
+        idx = s2i[bit]
+        rng = hi - lo + 1
+        hi = lo + (rng * cum[idx - 1]) // cum[0] - 1
+        lo = lo + (rng * cum[idx]) // cum[0]
+        while True:
+            if hi < 0x8000:
+                pass
+            elif lo >= 0x8000:
+                lo -= 0x8000
+                hi -= 0x8000
+            elif lo >= 0x4000 and hi < 0xC000:
+                lo -= 0x4000
+                hi -= 0x4000
+            else:
+                break
+            lo, hi = 2 * lo, 2 * hi + 1
+        if adaptive:
+            if cum[0] == 16383:
+                c = 0
+                for k in (3, 2, 1, 0):
+                    freq[k] = (freq[k] + 1) // 2
+                    cum[k] = c
+                    c += freq[k]
+            k = idx
+            while freq[k] == freq[k - 1]:
+                k -= 1
+            if k < idx:
+                sk, si = i2s[k], i2s[idx]
+                i2s[k], i2s[idx] = si, sk
+                s2i[sk], s2i[si] = idx, k
+            freq[k] += 1
+            while k > 0:
+                k -= 1
+                cum[k] += 1
+        out.append(bit)
+
+    for b in prefix:
+        code(b)
+    for _ in range(n_straddle):
+        rng = hi - lo + 1
+        # the symbol whose sub-interval contains the midpoint 0x8000 (falls back to bit 0 if that is EOF's)
+        pick = 0
+        for bit in (0, 1):
+            idx = s2i[bit]
+            h = lo + (rng * cum[idx - 1]) // cum[0] - 1
+            l = lo + (rng * cum[idx]) // cum[0]
+            if l < 0x8000 <= h:
+                pick = bit
+        code(pick)
+    for _ in range(64 if resolve else 0):
+        rng = hi - lo + 1
+        a = lo + (rng * cum[1]) // cum[0]          # index 1 (the more frequent symbol) owns [a, hi], index 2 [.., a-1]
+        if lo < 0x8000 <= hi and resolve == "up" and a > 0x8000 and s2i[0] != s2i[1]:
+            code(i2s[1])                           # midpoint inside index 2's part: index 1 lies above it
+            break
+        if lo < 0x8000 <= hi and resolve == "down" and a <= 0x8000:
+            code(i2s[2])                           # midpoint inside index 1's part: index 2 lies below it
+            break
+        code(i2s[1] if a <= 0x8000 else i2s[2])    # keep straddling
+    for b in tail:
+        code(b)
+    return np.array(out, dtype=np.uint8)

@@ -165,3 +165,25 @@ def test_lzmh_decoder_body_vs_golden_and_oracle(sim, oracle, golden):
         a = sim.lzmh_decode(junk.tobytes(), 512, cap=1 << 16)
         b = oracle.run_chain([ob.LZMH_DEC], junk, 512, out_cap=1 << 16)
         assert a == b
+
+
+@pytest.mark.parametrize("adaptive", [0, 1])
+def test_bac_carry_through_stored_words(sim, oracle, adaptive):
+    """Pending runs of 30..300 bits resolved upwards and downwards: the encoder's carry has to ripple through its
+    accumulator and through words already stored (CarryWriter::ripple in bac.cuh)."""
+    from conftest import straddling_bits
+    rng = np.random.default_rng(3 + adaptive)
+    ff = zz = 0
+    for n in (1, 2, 28, 29, 30, 31, 32, 33, 34, 40, 61, 62, 63, 64, 65, 66, 90, 127, 128, 129, 200, 300):
+        for tail in ([], [0], [1], [0, 0, 0], [1, 1, 1], list(rng.integers(0, 2, 40))):
+            for prefix, resolve in (((), "up"), ((), "down"), (tuple(rng.integers(0, 2, int(rng.integers(1, 70)))), None)):
+                bits = straddling_bits(n, tail, adaptive, prefix, resolve)
+                packed = np.packbits(bits)
+                want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=adaptive)
+                got = sim.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=adaptive)
+                assert got == want, (n, tail, prefix, resolve)
+                back = sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=adaptive)
+                assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
+                ff += b"\xff" * 6 in want[1]     # a run resolved downwards: 0111...
+                zz += b"\x00" * 6 in want[1]     # a run resolved by a carry: 1000...
+    assert adaptive == 0 or (ff > 20 and zz > 20)   # the static model cannot straddle for long (EOF owns the lowest third)
