@@ -130,7 +130,10 @@ struct BacModel
 //   decoder: o = value - lo; the symbol sits at index 2 when o < A.  nontop collects those bits, inv collects `top`
 //            for every position of the group (it changes for all later positions when the symbols trade places).
 // Out: dlo = what is added to lo, base - dlo = the new range.
-template <bool ADAPTIVE>
+// SWAP = false is for groups in which the symbols cannot trade places (freq[1] - freq[2] >= group length at the
+// start of the group): the update is then a single predicated increment of f_oth, and the caller adds the number
+// of index-1 symbols to f_top after the group.
+template <bool ADAPTIVE, bool SWAP>
 __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_t A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &dlo,
                                              uint32_t &base)
 {
@@ -138,12 +141,14 @@ __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_
   const bool is_top = (x & mask) == 0;
   dlo = is_top ? A : B;
   base = is_top ? rng : A;
-  const uint32_t top0 = m.top;   // the caller derives `top` from x at the end of the group
+  const uint32_t top0 = m.top, f_top0 = m.f_top;   // the caller derives `top` from x at the end of the group
   if (ADAPTIVE && m.bump(is_top))
     x = ~x;
   m.top = top0;
+  if (!SWAP)
+    m.f_top = f_top0;
 #else
-  if (ADAPTIVE)
+  if (ADAPTIVE && SWAP)
     asm("{\n\t"
         ".reg .pred pn, ps, pi;\n\t"
         ".reg .b32 t;\n\t"
@@ -160,6 +165,18 @@ __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_
         "}"
         : "=&r"(dlo), "=&r"(base), "+r"(m.f_top), "+r"(m.f_oth), "+r"(x)
         : "r"(mask), "r"(A), "r"(B), "r"(rng));
+  else if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %3, %4;\n\t"
+        "setp.ne.u32 pn, t, 0;\n\t"
+        "selp.u32 %0, %6, %5, pn;\n\t"
+        "selp.u32 %1, %5, %7, pn;\n\t"
+        "@pn add.u32 %2, %2, 1;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base), "+r"(m.f_oth)
+        : "r"(x), "r"(mask), "r"(A), "r"(B), "r"(rng));
   else
     asm("{\n\t"
         ".reg .pred pn;\n\t"
@@ -174,7 +191,7 @@ __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_
 #endif
 }
 
-template <bool ADAPTIVE>
+template <bool ADAPTIVE, bool SWAP>
 __device__ __forceinline__ void bac_pick_dec(uint32_t o, uint32_t bit, uint32_t A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &nontop,
                                              uint32_t &inv, uint32_t &dlo, uint32_t &base)
 {
@@ -184,12 +201,14 @@ __device__ __forceinline__ void bac_pick_dec(uint32_t o, uint32_t bit, uint32_t 
   base = is_top ? rng : A;
   if (!is_top)
     nontop |= bit;
-  const uint32_t top0 = m.top;   // the caller derives `top` from inv at the end of the group
+  const uint32_t top0 = m.top, f_top0 = m.f_top;   // the caller derives `top` from inv at the end of the group
   if (ADAPTIVE && m.bump(is_top))
     inv ^= bit - 1;
   m.top = top0;
+  if (!SWAP)
+    m.f_top = f_top0;
 #else
-  if (ADAPTIVE)
+  if (ADAPTIVE && SWAP)
     asm("{\n\t"
         ".reg .pred pn, ps, pi;\n\t"
         "setp.lt.u32 pn, %6, %8;\n\t"
@@ -205,6 +224,17 @@ __device__ __forceinline__ void bac_pick_dec(uint32_t o, uint32_t bit, uint32_t 
         "}"
         : "=&r"(dlo), "=&r"(base), "+r"(m.f_top), "+r"(m.f_oth), "+r"(nontop), "+r"(inv)
         : "r"(o), "r"(bit), "r"(A), "r"(B), "r"(rng), "r"(bit - 1));
+  else if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        "setp.lt.u32 pn, %4, %6;\n\t"
+        "selp.u32 %0, %7, %6, pn;\n\t"
+        "selp.u32 %1, %6, %8, pn;\n\t"
+        "@pn or.b32 %3, %3, %5;\n\t"
+        "@pn add.u32 %2, %2, 1;\n\t"
+        "}"
+        : "=&r"(dlo), "=&r"(base), "+r"(m.f_oth), "+r"(nontop)
+        : "r"(o), "r"(bit), "r"(A), "r"(B), "r"(rng));
   else
     asm("{\n\t"
         ".reg .pred pn;\n\t"
@@ -218,16 +248,19 @@ __device__ __forceinline__ void bac_pick_dec(uint32_t o, uint32_t bit, uint32_t 
 #endif
 }
 
-// Number of doublings (bac.c:112-137) of the interval (LO0, r1): LO0 = top-aligned low end, r1 = range.
-__device__ __forceinline__ uint32_t bac_doublings(uint32_t LO0, uint32_t r1)
+// Number of doublings (bac.c:112-137) of the interval (LO0, r1), PLUS ONE: LO0 = top-aligned low end, r1 = range.
+// n1 = leading bits on which lo and hi agree; below the first differing bit (lo 0, hi 1) the E3 run is where lo has 1
+// and hi has 0, i.e. where z = ~lo | hi is clear.  Masking z down to the bits below the first differing one leaves its
+// leading one at position n1 + 1 + n3.  The low 16 guard ones of z and of lo ^ hi bound both counts (n <= 16) for ANY
+// input, so a caller that lost bits (see the group redo in dega_device.cuh) cannot get a wild shift count.
+__device__ __forceinline__ uint32_t bac_doublings_p1(uint32_t LO0, uint32_t r1)
 {
   const uint32_t HI = LO0 + (r1 << 16) - 1;          // (hi << 16) | 0xFFFF; may wrap while bits are pending
   const uint32_t n1 = clz_nz(LO0 ^ HI);              // 0..16 (the low 16 bits of the xor are ones)
-  const uint32_t z = ~LO0 | HI;                      // clear exactly where lo has 1 and hi has 0
-  const uint32_t y = z << n1;
-  const uint32_t n3 = clz_nz(y + y);                 // run below the first differing bit, capped by the guard ones
-  return n1 + n3;                                    // <= 16
+  const uint32_t u = (~LO0 | HI) & (0x7FFFFFFFu >> n1);
+  return clz_nz(u);                                  // n + 1, 1..17
 }
+__device__ __forceinline__ uint32_t bac_doublings(uint32_t LO0, uint32_t r1) { return bac_doublings_p1(LO0, r1) - 1; }
 
 // ---------------------------------------------------------------------------------------------------
 // Output of the encoder: MSB-first bit stream whose tail can still take a carry.
@@ -353,7 +386,21 @@ struct BacEncoder
     LO = LO0 << n;
   }
 
-  // EncodeSymbol for a data bit (bac.c:107-111); c1 = cum[1]
+  // Same without the capacity test, for the unrolled groups: kg1 counts n + 1 per symbol and the CALLER checks after
+  // the group that the total stayed within a0 (else it redoes the group with narrow()).
+  __device__ __forceinline__ void narrow_fast(uint32_t dlo, uint32_t r1, uint32_t &kg1)
+  {
+    const uint64_t x = (((uint64_t)a0 << 32) | LO) + ((uint64_t)dlo << 16);
+    const uint32_t LO0 = (uint32_t)x;
+    const uint32_t c = bac_doublings_p1(LO0, r1);
+    const uint32_t n = c - 1;
+    kg1 += c;
+    rng = r1 << n;
+    a0 = __funnelshift_l(LO0, (uint32_t)(x >> 32), n);
+    LO = LO0 << n;
+  }
+
+  // EncodeSymbol for a data bit (bac.c:107-111); c1m1 = cum[1] - 1
   __device__ __forceinline__ void encode_bit(bool is_top, uint32_t c1m1, const DivEntry e, CarryWriter &w)
   {
     const uint32_t A = div_magic(rng * c1m1 + rng, e);

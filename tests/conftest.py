@@ -77,6 +77,8 @@ class Sim:
         L.sim_stage_run.restype = C.c_int
         L.sim_stage_run.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_float, C.c_int, C.c_void_p, C.c_uint64,
                                     C.POINTER(C.c_uint64)]
+        L.sim_bac_redo_count.restype = C.c_uint64
+        L.sim_bac_redo_count.argtypes = [C.c_int]
         L.sim_check_div_table.restype = C.c_uint64
         L.sim_check_div_table.argtypes = [C.c_uint32]
         L.sim_dega_encode_batch.restype = C.c_int

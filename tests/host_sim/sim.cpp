@@ -28,6 +28,9 @@ static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
+// how often the arithmetic coder's unrolled groups ran out of room and were redone (which = 0 encoder, 1 decoder)
+uint64_t sim_bac_redo_count(int which) { return g_bac_redo[which & 1]; }
+
 // exhaustive-ish check of the division table: returns the number of mismatches
 uint64_t sim_check_div_table(uint32_t stride)
 {

@@ -80,10 +80,14 @@ def test_bac_long_runs_force_halvings_and_pending_bits(sim, oracle):
     rng = np.random.default_rng(7)
     bits = np.concatenate([np.zeros(60000, np.uint8), (rng.random(80000) < 0.5).astype(np.uint8), np.ones(60000, np.uint8)])
     packed = np.packbits(bits)
+    redo0 = [sim.lib.sim_bac_redo_count(i) for i in (0, 1)]
     want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=1)
     got = sim.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=1)
     assert got == want
     assert sim.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=1)[1] == packed.tobytes()
+    # the first ones after 60000 zeros cost ~13 bits each: the unrolled 16-symbol groups run out of room (31 / 32 bits)
+    # and are redone symbol by symbol, in the encoder and in the decoder
+    assert all(sim.lib.sim_bac_redo_count(i) > redo0[i] for i in (0, 1))
 
 
 def test_bac_long_pending_runs(sim, oracle):
