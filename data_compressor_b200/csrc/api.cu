@@ -333,7 +333,9 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
     const uint64_t front_cap = kind == FRONT_DEGA ? seg_cap_bytes(max_len, vs) : fixed_cap_bytes(max_len, vs);
     const uint64_t bac_cap = kind == FRONT_DEGA ? bac_cap_bytes(front_cap, p->adaptive, boost) : 0;
     const uint64_t n_tiles = (n + 4095) / 4096;
-    const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(n_tiles + 2, 8) + Bump::size_of(2, 8) + Bump::size_of(n * front_cap, 1) +
+    // SEG scratch between front end and coder: word-interleaved per warp (bitio.cuh), so it covers whole warps
+    const uint64_t n_front = kind == FRONT_DEGA ? round_up(n, 32) : n;
+    const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(n_tiles + 2, 8) + Bump::size_of(2, 8) + Bump::size_of(n_front * front_cap, 1) +
                           Bump::size_of(n * bac_cap, 1) + 4096;
     int rc = arena_reserve(c, need);
     if (rc != DC_OK)
@@ -342,7 +344,7 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
     uint64_t *d_front_bits = b.take<uint64_t>(n);
     uint64_t *d_tiles = b.take<uint64_t>(n_tiles + 2);
     uint64_t *d_flags = b.take<uint64_t>(2);
-    uint8_t *d_front = b.take<uint8_t>(n * front_cap);
+    uint8_t *d_front = b.take<uint8_t>(n_front * front_cap);
     uint8_t *d_bac = b.take<uint8_t>(n * bac_cap);
 
     CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
@@ -361,6 +363,7 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
     fa.out.base = d_front;
     fa.out.stride_bytes = front_cap;
     fa.out.nbits = kind == FRONT_DEGA ? d_front_bits : d_bit_len;
+    fa.out.interleave = kind == FRONT_DEGA;
     fa.status = d_status;
     {
       Timed t(c, DC_K_FRONT);
@@ -380,6 +383,7 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
       ba.in.byte_off = nullptr;
       ba.in.stride_bytes = front_cap;
       ba.in.nbits = d_front_bits;
+      ba.in.interleave = 1;
       ba.out.base = d_bac;
       ba.out.stride_bytes = bac_cap;
       ba.out.nbits = d_bit_len;
@@ -439,14 +443,15 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
   const uint32_t vs = p->value_size_bits;
   const uint64_t seg_cap = kind == FRONT_DEGA ? seg_cap_bytes(max_len, vs) : 0;
   c->ev_mask = 0;
-  const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(2, 8) + Bump::size_of(n * seg_cap, 1) + 4096;
+  const uint64_t n_seg = round_up(n, 32);   // word-interleaved per warp (bitio.cuh)
+  const uint64_t need = Bump::size_of(n, 8) + Bump::size_of(2, 8) + Bump::size_of(n_seg * seg_cap, 1) + 4096;
   int rc = arena_reserve(c, need);
   if (rc != DC_OK)
     return rc;
   Bump b(c->arena);
   uint64_t *d_seg_bits = b.take<uint64_t>(n);
   uint64_t *d_flags = b.take<uint64_t>(2);
-  uint8_t *d_seg = b.take<uint8_t>(n * seg_cap);
+  uint8_t *d_seg = b.take<uint8_t>(n_seg * seg_cap);
 
   CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
   CU_TRY(c, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
@@ -472,6 +477,7 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
     ba.out.base = d_seg;
     ba.out.stride_bytes = seg_cap;
     ba.out.nbits = d_seg_bits;
+    ba.out.interleave = 1;
     ba.adaptive = p->adaptive;
     ba.div_table = c->d_div;
     ba.status = d_status;
@@ -486,6 +492,7 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
     ka.in.byte_off = nullptr;
     ka.in.stride_bytes = seg_cap;
     ka.in.nbits = d_seg_bits;
+    ka.in.interleave = 1;
     ka.in_seg = 1;
     ka.do_undiff = 1;
   }

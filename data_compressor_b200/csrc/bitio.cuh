@@ -16,12 +16,18 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 // A set of per-stream bit strings in one allocation.
 //   byte_off != nullptr : stream s starts at base + byte_off[s] (densely packed payload, any alignment)
 //   byte_off == nullptr : stream s starts at base + s * stride_bytes (scratch, stride multiple of 16)
+//   interleave != 0     : scratch between two kernels of one pipeline.  The 32 streams of a warp share a region of
+//                         32 * stride_bytes; word k of stream s sits at word (32 * k + s % 32) of the region of warp
+//                         s / 32, so that the lanes of a warp, which move through their streams at about the same
+//                         pace, touch the same 128-byte lines (coalesced loads and stores, whole lines leaving L2)
+//                         instead of 32 sectors 4.6 KB apart.  The allocation covers round_up(n, 32) streams.
 struct BitSrc
 {
   const uint8_t *base;
   const uint64_t *byte_off;
   uint64_t stride_bytes;
   const uint64_t *nbits;
+  uint32_t interleave;
 };
 
 struct BitDst
@@ -29,6 +35,7 @@ struct BitDst
   uint8_t *base;
   uint64_t stride_bytes;   // per-stream capacity, multiple of 16
   uint64_t *nbits;
+  uint32_t interleave;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -38,14 +45,16 @@ struct BitWriter
   uint32_t *words;
   uint32_t cap_words;
   uint32_t nwords;
+  uint32_t wstride;  // distance between consecutive words of the stream, in words (1, or 32 when interleaved)
   uint32_t nacc;     // pending bits in acc, always < 32 between calls
   uint64_t acc;      // low nacc bits are pending
   bool overflow;     // valid after finish(): the stream outgrew cap_words (nothing is ever written past the end)
 
-  __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes)
+  __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes, uint32_t word_stride = 1)
   {
     words = reinterpret_cast<uint32_t *>(p);
     cap_words = (uint32_t)(cap_bytes >> 2);
+    wstride = word_stride;
     nwords = 0;
     nacc = 0;
     acc = 0;
@@ -57,7 +66,7 @@ struct BitWriter
     nacc -= 32;
     const uint32_t w = (uint32_t)(acc >> nacc);
     if (nwords < cap_words)
-      words[nwords] = bswap32(w);
+      words[(uint64_t)nwords * wstride] = bswap32(w);
     nwords++;
   }
 
@@ -120,7 +129,7 @@ struct BitWriter
     const uint64_t total = bits();
     overflow = nwords + (nacc ? 1u : 0u) > cap_words;
     if (nacc && nwords < cap_words)
-      words[nwords] = bswap32((uint32_t)(acc << (32 - nacc)));
+      words[(uint64_t)nwords * wstride] = bswap32((uint32_t)(acc << (32 - nacc)));
     return total;
   }
 };
@@ -138,9 +147,11 @@ struct BitReader
   uint32_t wn;             // bits held in win
   uint32_t next;           // next 32-bit chunk to fetch
   uint32_t carry;          // BE(words[next]) when phase != 0
+  uint32_t wstride;        // distance between consecutive words of the stream, in words (1, or 32 when interleaved)
 
-  __device__ __forceinline__ void init(const uint8_t *p, uint64_t nbits_)
+  __device__ __forceinline__ void init(const uint8_t *p, uint64_t nbits_, uint32_t word_stride = 1)
   {
+    wstride = word_stride;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
     phase = (uint32_t)(a & 3) * 8;
@@ -163,11 +174,11 @@ struct BitReader
     {
       const uint64_t remaining = nbits - bitpos;
       if (phase == 0)
-        w = bswap32(__ldg(words + next));
+        w = bswap32(__ldg(words + (uint64_t)next * wstride));
       else
       {
         uint32_t nx = 0;
-        if (remaining > 32 - phase)            // the chunk really extends into the next aligned word
+        if (remaining > 32 - phase)            // the chunk really extends into the next aligned word (plain layout only)
           nx = bswap32(__ldg(words + next + 1));
         w = __funnelshift_l(nx, carry, phase);
         carry = nx;
@@ -223,10 +234,17 @@ struct BitReader
 
 __device__ __forceinline__ const uint8_t *src_ptr(const BitSrc &s, uint64_t i)
 {
+  if (s.interleave)
+    return s.base + (i >> 5) * 32 * s.stride_bytes + (i & 31) * 4;
   return s.base + (s.byte_off ? s.byte_off[i] : i * s.stride_bytes);
 }
 
-__device__ __forceinline__ uint8_t *dst_ptr(const BitDst &d, uint64_t i) { return d.base + i * d.stride_bytes; }
+__device__ __forceinline__ uint8_t *dst_ptr(const BitDst &d, uint64_t i)
+{
+  if (d.interleave)
+    return d.base + (i >> 5) * 32 * d.stride_bytes + (i & 31) * 4;
+  return d.base + i * d.stride_bytes;
+}
 
 // sign extension of the low vs bits (EXTEND_IO_INT_SIGN, DCLib/inc/io_macros.h:89-90)
 __device__ __forceinline__ int64_t sext(uint64_t v, uint32_t vs)

@@ -83,6 +83,15 @@ static inline long long __float2ll_rz(float v)
   return (long long)v;
 }
 static inline float __ll2float_rn(long long v) { return (float)v; }
+static inline float __int2float_rn(int v) { return (float)v; }
+static inline unsigned int __float2uint_rz(float v)
+{
+  if (!(v > 0.0f))
+    return 0u;
+  if (v >= 4294967296.0f)
+    return 0xFFFFFFFFu;
+  return (unsigned int)v;
+}
 static inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v)
 {
   const unsigned long long o = *p;

@@ -241,7 +241,7 @@ int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t ch
   const uint64_t max_len = std::min(bl, channel_len);
   const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
   const uint64_t bac_cap = round_up(seg_cap * 13 / 8 + 64, 16);
-  std::vector<uint8_t> seg(n * seg_cap + 16), bac(n * bac_cap + 16);
+  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 16), bac(n * bac_cap + 16);   // SEG scratch: interleaved per warp
   std::vector<uint64_t> seg_bits(n);
   unsigned long long flag = 0;
   for (uint64_t s = 0; s < n; s++)
@@ -253,13 +253,13 @@ int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t ch
   fa.in_is_float = fa.do_norm = fa.do_diff = fa.out_seg = 1;
   fa.vs = vs;
   fa.nf = nf;
-  fa.out = BitDst{ seg.data(), seg_cap, seg_bits.data() };
+  fa.out = BitDst{ seg.data(), seg_cap, seg_bits.data(), 1 };
   fa.status = status;
   BacArgs ba;
   memset(&ba, 0, sizeof(ba));
   ba.n_streams = n;
-  ba.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data() };
-  ba.out = BitDst{ bac.data(), bac_cap, bit_len };
+  ba.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data(), 1 };
+  ba.out = BitDst{ bac.data(), bac_cap, bit_len, 0 };
   ba.adaptive = adaptive;
   ba.div_table = div_table();
   ba.status = status;
@@ -299,7 +299,7 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
   const uint64_t n = L.n_streams;
   const uint64_t max_len = std::min(bl, channel_len);
   const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
-  std::vector<uint8_t> seg(n * seg_cap + 16);
+  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 16);   // interleaved per warp
   std::vector<uint64_t> seg_bits(n);
   // the payload is copied into a padded buffer: the reader may touch the aligned word after the last byte
   std::vector<uint8_t> pay(byte_off[n] + 16, 0);
@@ -311,7 +311,7 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
   memset(&ba, 0, sizeof(ba));
   ba.n_streams = n;
   ba.in = BitSrc{ pay.data(), byte_off, 0, bit_len };
-  ba.out = BitDst{ seg.data(), seg_cap, seg_bits.data() };
+  ba.out = BitDst{ seg.data(), seg_cap, seg_bits.data(), 1 };
   ba.adaptive = adaptive;
   ba.div_table = div_table();
   ba.status = status;
@@ -320,7 +320,7 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
   memset(&ka, 0, sizeof(ka));
   ka.lay = L;
   ka.n_streams = n;
-  ka.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data() };
+  ka.in = BitSrc{ seg.data(), nullptr, seg_cap, seg_bits.data(), 1 };
   ka.in_seg = ka.do_undiff = ka.do_denorm = 1;
   ka.vs = vs;
   ka.nf = nf;
