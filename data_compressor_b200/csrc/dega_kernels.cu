@@ -53,12 +53,13 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
     back_body(a, s);
 }
 
+template <bool NARROW>
 __global__ void __launch_bounds__(128, 16) back_dega_kernel(const BackArgs a)
 {
-  __shared__ float stage[128 * 4];   // four decoded samples per thread, leaving as one 128-bit store
+  __shared__ float stage[128 * kBackStage];   // decoded samples per thread, leaving as 128-bit stores of whole sectors
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < a.n_streams)
-    back_dega_body(a, s, stage + threadIdx.x * 4);
+    back_dega_body<NARROW>(a, s, stage + threadIdx.x * kBackStage);
 }
 
 void launch_back(const BackArgs &a, cudaStream_t st)
@@ -70,7 +71,12 @@ void launch_back(const BackArgs &a, cudaStream_t st)
   // the specialised kernel reads the 4-byte aligned SEG scratch (fixed stride); anything else takes the general one
   if (a.in_seg && a.do_undiff && a.do_denorm && a.vs >= 17 && a.in.byte_off == nullptr && (a.in.stride_bytes & 3) == 0 &&
       (reinterpret_cast<uintptr_t>(a.in.base) & 3) == 0)
-    back_dega_kernel<<<grid, block, 0, st>>>(a);
+  {
+    if (a.vs <= 32 && a.in.stride_bytes < (1ull << 28))   // every stream shorter than 2^31 bits
+      back_dega_kernel<true><<<grid, block, 0, st>>>(a);
+    else
+      back_dega_kernel<false><<<grid, block, 0, st>>>(a);
+  }
   else
     back_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;

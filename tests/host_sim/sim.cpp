@@ -62,7 +62,7 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
   const bool float_out = stage == DC_STAGE_DENORMALIZE || stage == DC_STAGE_DEGA_DEC;
   const uint64_t n_in = float_in ? in_bits / 32 : in_bits / vs;
 
-  std::vector<uint8_t> h_in(round_up(in_bytes, 16) + 64, 0);
+  std::vector<uint8_t> h_in(round_up(in_bytes, 16) + 4096, 0);
   if (in_bytes)
     memcpy(h_in.data(), in, in_bytes);
   uint64_t meta[8] = { in_bits, 0, 0, 0, 0, 0, 0, 0 };
@@ -94,7 +94,7 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       case DC_STAGE_DEGA_DEC: mid_cap = round_up((in_bytes * 4 + 4096) * boost, 16); out_dev = round_up(mid_cap * 8 * 4 + 16, 16); break;
       default: return DC_ERR_INVALID_VALUE;
     }
-    std::vector<uint8_t> h_mid(mid_cap + 16, 0), h_out(out_dev + 16, 0);
+    std::vector<uint8_t> h_mid(mid_cap + 4096, 0), h_out(out_dev + 16, 0);   // the back end reads one word ahead
     memset(meta + 1, 0, 7 * sizeof(uint64_t));
 
     const bool is_front = stage == DC_STAGE_NORMALIZE || stage == DC_STAGE_DIFF_ENC || stage == DC_STAGE_SEG_ENC || stage == DC_STAGE_DEGA_ENC;
@@ -181,8 +181,11 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       ka.status = status;
       if (ka.in_seg && ka.do_undiff && ka.do_denorm && ka.vs >= 17)
       {
-        float stage4[4];
-        back_dega_body(ka, 0, stage4);
+        float stage4[kBackStage];
+        if (ka.vs <= 32)
+          back_dega_body<true>(ka, 0, stage4);
+        else
+          back_dega_body<false>(ka, 0, stage4);
       }
       else
         back_body(ka, 0);
@@ -241,7 +244,7 @@ int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t ch
   const uint64_t max_len = std::min(bl, channel_len);
   const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
   const uint64_t bac_cap = round_up(seg_cap * 13 / 8 + 64, 16);
-  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 16), bac(n * bac_cap + 16);   // SEG scratch: interleaved per warp
+  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 4096), bac(n * bac_cap + 16);   // SEG scratch: interleaved per warp
   std::vector<uint64_t> seg_bits(n);
   unsigned long long flag = 0;
   for (uint64_t s = 0; s < n; s++)
@@ -299,7 +302,7 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
   const uint64_t n = L.n_streams;
   const uint64_t max_len = std::min(bl, channel_len);
   const uint64_t seg_cap = round_up((max_len * (2ull * vs + 1) + 7) / 8 + 8, 16);
-  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 16);   // interleaved per warp
+  std::vector<uint8_t> seg(round_up(n, 32) * seg_cap + 4096);   // interleaved per warp
   std::vector<uint64_t> seg_bits(n);
   // the payload is copied into a padded buffer: the reader may touch the aligned word after the last byte
   std::vector<uint8_t> pay(byte_off[n] + 16, 0);
@@ -335,8 +338,11 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
       bac_decode_body<false>(ba, s, div_table());
     if (vs >= 17)
     {
-      float stage4[4];
-      back_dega_body(ka, s, stage4);
+      float stage4[kBackStage];
+      if (vs <= 32)
+        back_dega_body<true>(ka, s, stage4);
+      else
+        back_dega_body<false>(ka, s, stage4);
     }
     else
       back_body(ka, s);
