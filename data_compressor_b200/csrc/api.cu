@@ -21,6 +21,7 @@ struct dc_ctx
   int device;
   cudaStream_t stream;
   DivEntry *d_div;
+  unsigned int *d_work;  // work counter of the coder kernels' warp-task scheduler
   uint8_t *arena;        // kernel scratch (SEG / coder strides), grown on demand
   uint64_t arena_size;
   uint8_t *stage;        // device staging of the host-buffer calls (samples, payload, index), grown on demand
@@ -389,6 +390,7 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
       ba.out.nbits = d_bit_len;
       ba.adaptive = p->adaptive;
       ba.div_table = c->d_div;
+      ba.work = c->d_work;
       ba.status = d_status;
       ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_flags);
       {
@@ -480,6 +482,7 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
     ba.out.interleave = 1;
     ba.adaptive = p->adaptive;
     ba.div_table = c->d_div;
+      ba.work = c->d_work;
     ba.status = d_status;
     ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_flags);
     {
@@ -544,6 +547,7 @@ int dc_create(dc_ctx **out, int device)
   build_div_table(tab.data());
   if (cudaMalloc(&c->d_div, kDivTableEntries * sizeof(DivEntry)) != cudaSuccess ||
       cudaMemcpy(c->d_div, tab.data(), kDivTableEntries * sizeof(DivEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&c->d_work, 256) != cudaSuccess ||
       cudaMallocHost(&c->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess)
   {
     cudaGetLastError();
@@ -586,6 +590,8 @@ void dc_destroy(dc_ctx *c)
     cudaFree(c->stage);
   if (c->d_div)
     cudaFree(c->d_div);
+  if (c->d_work)
+    cudaFree(c->d_work);
   if (c->h_pinned)
     cudaFreeHost(c->h_pinned);
   for (int i = 0; i < 2 * DC_K_COUNT; i++)
@@ -744,13 +750,16 @@ int dc_axdr_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_
 
 // ---- DEGA, host buffers ----------------------------------------------------------------------------------
 // Channel chunks of the host-buffer calls: the copy of chunk k+1 (and the copy-back of chunk k-1) overlaps the kernels
-// of chunk k.  A chunk keeps at least one full wave of coder CTAs (148 SMs x 1024 streams); ragged layouts use one.
+// of chunk k.  These calls are bound by the PCIe copies (1.4 GB in, 0.5 GB out for config 2 against ~15 ms of kernels),
+// so chunks are sized for copy overlap rather than for full coder waves: a quarter wave (37 888 streams) still gives
+// every SM eight warps through the warp-task scheduler, and eight chunks expose only 1/8 of the first copy in and of
+// the last copy out.  Ragged layouts use one chunk.
 static int host_chunks(const Layout &L, uint64_t n_channels)
 {
   if (L.sample_off != nullptr || n_channels < 2)
     return 1;
-  const uint64_t wave = 148ull * 1024;
-  uint64_t k = L.n_streams / wave;
+  const uint64_t quarter_wave = 148ull * 256;
+  uint64_t k = L.n_streams / quarter_wave;
   if (k > 8)
     k = 8;
   if (k > n_channels)
@@ -1265,6 +1274,7 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       ba.out.nbits = d_meta + 2;
       ba.adaptive = params->adaptive;
       ba.div_table = c->d_div;
+      ba.work = c->d_work;
       ba.status = d_status;
       ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_meta + 5);
       launch_bac_encode(ba, c->stream);
@@ -1280,6 +1290,7 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       ba.out.nbits = stage == DC_STAGE_BAC_DEC ? d_meta + 2 : d_meta + 1;
       ba.adaptive = params->adaptive;
       ba.div_table = c->d_div;
+      ba.work = c->d_work;
       ba.status = d_status;
       ba.overflow_flag = reinterpret_cast<unsigned long long *>(d_meta + 5);
       launch_bac_decode(ba, c->stream);

@@ -294,15 +294,38 @@ __device__ __forceinline__ void load_div_table(DivEntry *smem, const DivEntry *g
   __syncthreads();
 }
 
+// Work distribution: a stream is one long sequential task (milliseconds), so what matters is that the last, partial
+// round of tasks is spread over all SMs instead of filling a few of them: resident CTAs (one per SM), and every warp
+// fetches its next 32 streams from a device counter.  Warps of a thin last round then run with few neighbours and
+// finish several times faster than in a full SM, which takes most of the sting out of stream counts that are not a
+// multiple of 148 * 1024.
+template <typename Body>
+__device__ __forceinline__ void bac_warp_tasks(const BacArgs &a, Body body)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t n_tasks = (a.n_streams + 31) / 32;
+  for (;;)
+  {
+    uint32_t w = 0;
+    if (lane == 0)
+      w = atomicAdd(a.work, 1u);
+    w = __shfl_sync(0xFFFFFFFFu, w, 0);
+    if (w >= n_tasks)
+      break;
+    const uint64_t s = (uint64_t)w * 32 + lane;
+    if (s < a.n_streams)
+      body(s);
+    __syncwarp();
+  }
+}
+
 template <bool ADAPTIVE>
 __global__ void __launch_bounds__(kBacThreads, 1) bac_encode_kernel(const BacArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < a.n_streams)
-    bac_encode_body<ADAPTIVE>(a, s, tab);
+  bac_warp_tasks(a, [&](uint64_t s) { bac_encode_body<ADAPTIVE>(a, s, tab); });
 }
 
 template <bool ADAPTIVE>
@@ -311,9 +334,20 @@ __global__ void __launch_bounds__(kBacThreads, 1) bac_decode_kernel(const BacArg
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < a.n_streams)
-    bac_decode_body<ADAPTIVE>(a, s, tab);
+  bac_warp_tasks(a, [&](uint64_t s) { bac_decode_body<ADAPTIVE>(a, s, tab); });
+}
+
+static int sm_count()
+{
+  static int n = 0;
+  if (n == 0)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 template <typename K>
@@ -322,7 +356,9 @@ static void launch_bac(K kernel, const BacArgs &a, cudaStream_t st)
   if (a.n_streams == 0)
     return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bac_smem_bytes());
-  const unsigned grid = (unsigned)((a.n_streams + kBacThreads - 1) / kBacThreads);
+  cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
+  const uint64_t want = (a.n_streams + kBacThreads - 1) / kBacThreads;
+  const unsigned grid = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
   kernel<<<grid, kBacThreads, bac_smem_bytes(), st>>>(a);
   g_launches++;
 }

@@ -128,6 +128,7 @@ struct BacArgs
   const DivEntry *div_table;   // device copy
   int32_t *status;             // in/out: streams with status != 0 are skipped (out bits = 0)
   unsigned long long *overflow_flag;   // set to 1 when any stream outgrew its output stride (may be nullptr)
+  unsigned int *work;          // device counter of the warp-task scheduler (zeroed by the launcher)
 };
 void launch_bac_encode(const BacArgs &a, cudaStream_t st);
 void launch_bac_decode(const BacArgs &a, cudaStream_t st);
