@@ -366,6 +366,7 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
     fa.out.nbits = kind == FRONT_DEGA ? d_front_bits : d_bit_len;
     fa.out.interleave = kind == FRONT_DEGA;
     fa.status = d_status;
+    fa.work = c->d_work;
     {
       Timed t(c, DC_K_FRONT);
       launch_front(fa, c->stream);
@@ -467,6 +468,7 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
   ka.samples = d_samples;
   ka.n_out = d_n_out;
   ka.status = d_status;
+  ka.work = c->d_work;
   ka.do_denorm = 1;
   if (kind == FRONT_DEGA)
   {
@@ -1253,6 +1255,8 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       fa.out.stride_bytes = stage == DC_STAGE_DEGA_ENC ? mid_cap : out_cap_dev;
       fa.out.nbits = stage == DC_STAGE_DEGA_ENC ? d_meta + 1 : d_meta + 2;
       fa.status = d_status;
+      fa.work = c->d_work;
+    fa.work = c->d_work;
       launch_front(fa, c->stream);
     }
     if (stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC)
@@ -1325,6 +1329,8 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       ka.out.nbits = d_meta + 2;
       ka.n_out = d_meta + 3;
       ka.status = d_status;
+      ka.work = c->d_work;
+  ka.work = c->d_work;
       launch_back(ka, c->stream);
     }
     if ((rc = check_launch(c, "stage kernels")) != DC_OK)

@@ -14,6 +14,53 @@ static uint64_t g_launches = 0;
 uint64_t launch_counter() { return g_launches; }
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
+// Work distribution of the stream-per-thread kernels: a stream is one long sequential task (up to milliseconds), so
+// what matters is that the last, partial round of tasks is spread over all SMs instead of filling a few of them:
+// resident CTAs, and every warp fetches its next 32 streams from a device counter.  Warps of a thin last round then
+// run with few neighbours and finish several times faster than in a full SM, which takes most of the sting out of
+// stream counts that are not a multiple of what the GPU holds at once (and lets each kernel pick its occupancy by
+// register need, not by wave arithmetic).
+template <typename Body>
+__device__ __forceinline__ void warp_tasks(unsigned int *work, uint64_t n_streams, Body body)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t n_tasks = (n_streams + 31) / 32;
+  for (;;)
+  {
+    uint32_t w = 0;
+    if (lane == 0)
+      w = atomicAdd(work, 1u);
+    w = __shfl_sync(0xFFFFFFFFu, w, 0);
+    if (w >= n_tasks)
+      break;
+    const uint64_t s = (uint64_t)w * 32 + lane;
+    if (s < n_streams)
+      body(s);
+    __syncwarp();
+  }
+}
+
+static int sm_count()
+{
+  static int n = 0;
+  if (n == 0)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// grid of a resident launch: ctas_per_sm CTAs on every SM, fewer when there is less work
+static unsigned resident_grid(uint64_t n_streams, unsigned block, unsigned ctas_per_sm)
+{
+  const uint64_t want = (n_streams + block - 1) / block;
+  const uint64_t cap = (uint64_t)sm_count() * ctas_per_sm;
+  return (unsigned)(want < cap ? want : cap);
+}
+
 __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
 {
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,14 +69,13 @@ __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
 }
 
 #ifndef FRONT_MIN_CTAS
-#define FRONT_MIN_CTAS 12
+#define FRONT_MIN_CTAS 6
 #endif
-// CTAs of 128 threads; FRONT_MIN_CTAS bounds the register count (16 -> 32 registers would spill the prefetch buffers)
+// Resident CTAs of 128 threads fed by the warp-task scheduler; measured 0.93 ms at 6 CTAs per SM (48 registers, no
+// spills), 1.02 at 10, 1.12 at 12, 1.30 at 16 (spills): the kernel is issue bound, extra warps only add pressure
 __global__ void __launch_bounds__(128, FRONT_MIN_CTAS) front_dega_kernel(const FrontArgs a)
 {
-  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < a.lay.n_streams)
-    front_dega_body(a, s);
+  warp_tasks(a.work, a.lay.n_streams, [&](uint64_t s) { front_dega_body(a, s); });
 }
 
 void launch_front(const FrontArgs &a, cudaStream_t st)
@@ -39,7 +85,10 @@ void launch_front(const FrontArgs &a, cudaStream_t st)
   const unsigned block = 128;
   const unsigned grid = (unsigned)((a.lay.n_streams + block - 1) / block);
   if (a.in_is_float && a.do_norm && a.do_diff && a.out_seg)
-    front_dega_kernel<<<grid, block, 0, st>>>(a);
+  {
+    cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
+    front_dega_kernel<<<resident_grid(a.lay.n_streams, block, FRONT_MIN_CTAS), block, 0, st>>>(a);
+  }
   else
     front_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;
@@ -53,13 +102,16 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
     back_body(a, s);
 }
 
+// measured 1.32 ms at 10 CTAs per SM, 1.38 at 8, 1.36 at 12, 1.46 at 16
+#ifndef BACK_MIN_CTAS
+#define BACK_MIN_CTAS 10
+#endif
 template <bool NARROW>
-__global__ void __launch_bounds__(128, 16) back_dega_kernel(const BackArgs a)
+__global__ void __launch_bounds__(128, BACK_MIN_CTAS) back_dega_kernel(const BackArgs a)
 {
   __shared__ float stage[128 * kBackStage];   // decoded samples per thread, leaving as 128-bit stores of whole sectors
-  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < a.n_streams)
-    back_dega_body<NARROW>(a, s, stage + threadIdx.x * kBackStage);
+  float *mine = stage + threadIdx.x * kBackStage;
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { back_dega_body<NARROW>(a, s, mine); });
 }
 
 void launch_back(const BackArgs &a, cudaStream_t st)
@@ -72,10 +124,12 @@ void launch_back(const BackArgs &a, cudaStream_t st)
   if (a.in_seg && a.do_undiff && a.do_denorm && a.vs >= 17 && a.in.byte_off == nullptr && (a.in.stride_bytes & 3) == 0 &&
       (reinterpret_cast<uintptr_t>(a.in.base) & 3) == 0)
   {
+    cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
+    const unsigned rgrid = resident_grid(a.n_streams, block, BACK_MIN_CTAS);
     if (a.vs <= 32 && a.in.stride_bytes < (1ull << 28))   // every stream shorter than 2^31 bits
-      back_dega_kernel<true><<<grid, block, 0, st>>>(a);
+      back_dega_kernel<true><<<rgrid, block, 0, st>>>(a);
     else
-      back_dega_kernel<false><<<grid, block, 0, st>>>(a);
+      back_dega_kernel<false><<<rgrid, block, 0, st>>>(a);
   }
   else
     back_kernel<<<grid, block, 0, st>>>(a);
@@ -294,38 +348,13 @@ __device__ __forceinline__ void load_div_table(DivEntry *smem, const DivEntry *g
   __syncthreads();
 }
 
-// Work distribution: a stream is one long sequential task (milliseconds), so what matters is that the last, partial
-// round of tasks is spread over all SMs instead of filling a few of them: resident CTAs (one per SM), and every warp
-// fetches its next 32 streams from a device counter.  Warps of a thin last round then run with few neighbours and
-// finish several times faster than in a full SM, which takes most of the sting out of stream counts that are not a
-// multiple of 148 * 1024.
-template <typename Body>
-__device__ __forceinline__ void bac_warp_tasks(const BacArgs &a, Body body)
-{
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t n_tasks = (a.n_streams + 31) / 32;
-  for (;;)
-  {
-    uint32_t w = 0;
-    if (lane == 0)
-      w = atomicAdd(a.work, 1u);
-    w = __shfl_sync(0xFFFFFFFFu, w, 0);
-    if (w >= n_tasks)
-      break;
-    const uint64_t s = (uint64_t)w * 32 + lane;
-    if (s < a.n_streams)
-      body(s);
-    __syncwarp();
-  }
-}
-
 template <bool ADAPTIVE>
 __global__ void __launch_bounds__(kBacThreads, 1) bac_encode_kernel(const BacArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  bac_warp_tasks(a, [&](uint64_t s) { bac_encode_body<ADAPTIVE>(a, s, tab); });
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { bac_encode_body<ADAPTIVE>(a, s, tab); });
 }
 
 template <bool ADAPTIVE>
@@ -334,20 +363,7 @@ __global__ void __launch_bounds__(kBacThreads, 1) bac_decode_kernel(const BacArg
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  bac_warp_tasks(a, [&](uint64_t s) { bac_decode_body<ADAPTIVE>(a, s, tab); });
-}
-
-static int sm_count()
-{
-  static int n = 0;
-  if (n == 0)
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { bac_decode_body<ADAPTIVE>(a, s, tab); });
 }
 
 template <typename K>
@@ -357,9 +373,7 @@ static void launch_bac(K kernel, const BacArgs &a, cudaStream_t st)
     return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bac_smem_bytes());
   cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
-  const uint64_t want = (a.n_streams + kBacThreads - 1) / kBacThreads;
-  const unsigned grid = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
-  kernel<<<grid, kBacThreads, bac_smem_bytes(), st>>>(a);
+  kernel<<<resident_grid(a.n_streams, kBacThreads, 1), kBacThreads, bac_smem_bytes(), st>>>(a);
   g_launches++;
 }
 

@@ -75,6 +75,7 @@ struct FrontArgs
   float nf;
   BitDst out;
   int32_t *status;
+  unsigned int *work;       // device counter of the warp-task scheduler (specialised kernel; zeroed by the launcher)
 };
 void launch_front(const FrontArgs &a, cudaStream_t st);
 
@@ -115,6 +116,7 @@ struct BackArgs
   BitDst out;
   uint64_t *n_out;          // values produced per stream
   int32_t *status;
+  unsigned int *work;       // device counter of the warp-task scheduler (specialised kernel; zeroed by the launcher)
 };
 void launch_back(const BackArgs &a, cudaStream_t st);
 
