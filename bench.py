@@ -42,7 +42,7 @@ class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons DURING the timed region through NVML (in-process: the nvidia-smi CLI in
     loop mode stalls the driver for milliseconds per sample, which showed up as 5-10 ms of extra step time)."""
 
-    def __init__(self, gpu_index, period=0.05):
+    def __init__(self, gpu_index, period=0.1):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.period = period
@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
         # NVML clocks-event-reason bits (nvml.h): 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal
         names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(v for k, v in names.items() if bits & k),
-                "samples": len(sm), "how": "NVML, 50 ms period, during the timed region"}
+                "samples": len(sm), "how": "NVML, 100 ms period, during the timed region"}
 
 
 def measured_peak():
@@ -324,8 +324,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dom_ms,
-                "note": "the coder is sequential per stream and bound by integer issue (ALU + FMA-heavy pipes ~70-88 %, DRAM < 3 %): "
-                        "DESIGN.md 3.1, profiles/r1d_dega_ncu_summary.txt"}
+                "note": "the coder is sequential per stream and bound by integer instruction issue (~1.9 cycles per integer instruction per scheduler, profiles/r1_ubench_pipes.txt; DRAM < 4 %): "
+                        "DESIGN.md 3.1, profiles/r1g_dega_ncu_summary.txt"}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cpu = None
