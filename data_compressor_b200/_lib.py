@@ -74,6 +74,7 @@ SYMBOLS = {
     "dc_axdr_decode_device": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
     "dc_lzmh_encode_device": (_I, [_P, _P, _P, _U64, _P, _U64, _P, _P, _P, _PU64]),
     "dc_lzmh_decode_device": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _P, _P, _P]),
+    "dc_aggregate_device": (_I, [_P, _P, _U64, _U64, C.c_uint32, _P]),
     "dc_stage_run_host": (_I, [_P, _I, _P, _U64, _PP, _P, _U64, _PU64]),
     "dc_stage_out_bound": (_U64, [_I, _U64, _PP]),
 }

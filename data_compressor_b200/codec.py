@@ -166,6 +166,20 @@ class Context:
     def axdr_decode(self, enc: Encoded, vs: int = 32, nf: float = 100.0, out: torch.Tensor | None = None):
         return self._decode(self.lib.dc_axdr_decode_device, "dc_axdr_decode_device", enc, vs, nf, False, out)
 
+    # ---- aggregate: granularity reduction ---------------------------------------------------------
+    def aggregate(self, x: torch.Tensor, num_values: int) -> torch.Tensor:
+        """`encode aggregate num_values=k` (DCLib/src/aggregate.c:9-27) for every channel of a float32
+        [n_channels, channel_len] tensor: sums of k consecutive samples, added left to right; the last group of a
+        channel may be short.  Returns [n_channels, ceil(channel_len / k)]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and num_values >= 1
+        nc, cl = x.shape
+        out = torch.empty((nc, (cl + num_values - 1) // num_values), dtype=torch.float32, device=x.device)
+        torch.cuda.current_stream(x.device).synchronize()
+        rc = self.lib.dc_aggregate_device(self.h, x.data_ptr(), nc, cl, int(num_values), out.data_ptr())
+        self._check(rc, "dc_aggregate_device")
+        self.synchronize()
+        return out
+
     # ---- LZMH: independent byte blocks ------------------------------------------------------------
     def lzmh_encode(self, data: torch.Tensor, block_bytes: int = 65536, payload_cap: int | None = None):
         """`encode lzmh` for every block of `block_bytes` bytes of a uint8 tensor (last block may be short).

@@ -750,6 +750,16 @@ int dc_axdr_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_
                               d_status);
 }
 
+// ---- aggregate -------------------------------------------------------------------------------------------
+int dc_aggregate_device(dc_ctx *c, const float *d_samples, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *d_out)
+{
+  if (!c || num_values == 0 || (n_channels * channel_len != 0 && (!d_samples || !d_out)))
+    return DC_ERR_INVALID_VALUE;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  launch_aggregate(d_samples, n_channels, channel_len, num_values, d_out, c->stream);
+  return check_launch(c, "aggregate_kernel");
+}
+
 // ---- DEGA, host buffers ----------------------------------------------------------------------------------
 // Channel chunks of the host-buffer calls: the copy of chunk k+1 (and the copy-back of chunk k-1) overlaps the kernels
 // of chunk k.  These calls are bound by the PCIe copies (1.4 GB in, 0.5 GB out for config 2 against ~15 ms of kernels),

@@ -332,6 +332,41 @@ void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Aggregate (DCLib/src/aggregate.c:9-27): float32 sums of num_values consecutive samples per channel, added strictly
+// left to right starting from 0.0f (the reference's `sum += value` loop), the last group of a channel may be short.
+// One thread per output value; the groups of a warp are contiguous in memory, and each lane re-uses every 32-byte
+// sector it touches for eight samples out of L1.  Memory bound: 4 B read per sample, 4 B written per group.
+__global__ void __launch_bounds__(256) aggregate_kernel(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values,
+                                                        uint64_t groups_per_channel, float *out)
+{
+  const uint64_t total = n_channels * groups_per_channel;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint64_t c = g / groups_per_channel;
+    const uint64_t first = (g - c * groups_per_channel) * num_values;
+    const uint64_t count = channel_len - first < num_values ? channel_len - first : num_values;
+    const float *src = in + c * channel_len + first;
+    float sum = 0.0f;
+    for (uint64_t i = 0; i < count; i++)
+      sum = __fadd_rn(sum, __ldg(src + i));
+    out[g] = sum;
+  }
+}
+
+void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *out, cudaStream_t st)
+{
+  const uint64_t groups = (channel_len + num_values - 1) / num_values;
+  const uint64_t total = n_channels * groups;
+  if (total == 0)
+    return;
+  const unsigned block = 256;
+  const uint64_t want = (total + block - 1) / block;
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  aggregate_kernel<<<(unsigned)(want < cap ? want : cap), block, 0, st>>>(in, n_channels, channel_len, num_values, groups, out);
+  g_launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Arithmetic coder kernels.  The 128 KiB division table lives in shared memory (one copy per CTA, one CTA of
 // kBacThreads threads per SM); before the first halving every lane of a warp has coded the same number of
 // symbols, so `total` is warp-uniform and the table read is a broadcast.

@@ -143,6 +143,9 @@ void launch_byte_scan(const uint64_t *nbits, uint64_t n, uint64_t *byte_off, uin
 void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t *nbits, const uint64_t *byte_off,
                    uint64_t n, uint8_t *payload, uint64_t payload_cap, cudaStream_t st);
 
+// ---- aggregate (granularity reduction): out[c][g] = sum of in[c][g*k .. g*k+k), strictly sequential float32 adds
+void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *out, cudaStream_t st);
+
 // ---- LZMH ------------------------------------------------------------------------------------------------
 struct LzmhArgs
 {

@@ -161,6 +161,16 @@ int dc_lzmh_decode_device(dc_ctx *ctx, const uint8_t *d_payload, uint64_t payloa
                           const uint64_t *d_bit_len, const uint64_t *d_byte_off, uint64_t n_streams,
                           uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status);
 
+/* ---- batch face: aggregate (granularity reduction) ------------------------------------------ */
+
+/* DCLib/src/aggregate.c:9-27 (`encode aggregate num_values=k`) for n_channels channels of channel_len
+   float32 samples each (device pointers, channel-major): out[c][g] = in[c][g*k] + in[c][g*k+1] + ...
+   added strictly left to right starting from 0.0f, like the reference's loop; the last group of a
+   channel may be short (aggregate.c:21-22).  d_out holds n_channels * ceil(channel_len / k) floats.
+   Used to derive 1 min / 15 min series from 1 s data on the device (BASELINE.json configs[4]). */
+int dc_aggregate_device(dc_ctx *ctx, const float *d_samples, uint64_t n_channels, uint64_t channel_len,
+                        uint32_t num_values, float *d_out);
+
 /* ---- plugin face: one stage, one stream, host buffers -------------------------------------- */
 /* What an enc_dec_function_t body (DCLib/inc/enc_dec.h:11) calls after draining its input bit
    buffer: runs ONE reference stage on the GPU over `in_bits` bits and returns the exact output bit

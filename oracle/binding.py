@@ -60,6 +60,8 @@ class Oracle:
         L.dco_run_chain.restype = C.c_int
         L.dco_run_chain.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_uint64, C.c_uint, C.c_float,
                                     C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.dco_aggregate.restype = C.c_uint64
+        L.dco_aggregate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p]
         L.dco_dega_encode_batch.restype = C.c_int64
         L.dco_dega_encode_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_float, C.c_int]
 
@@ -85,6 +87,13 @@ class Oracle:
         rc, raw, nb = self.run_chain(DEGA_DEC, payload, nbits, vs, nf, adaptive, out_cap=out_cap)
         return rc, np.frombuffer(raw[: (nb // 32) * 4], dtype=np.float32).copy()
 
+    def aggregate(self, samples, num_values: int) -> np.ndarray:
+        """`encode aggregate num_values=k` on one channel (aggregate.c:9-27)."""
+        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        out = np.empty((x.size + num_values - 1) // num_values + 1, dtype=np.float32)
+        n = int(self.lib.dco_aggregate(x.ctypes.data if x.size else None, x.size, int(num_values), out.ctypes.data))
+        return out[:n].copy()
+
     def dega_encode_batch(self, samples2d, vs=32, nf=100.0, adaptive=1) -> int:
         x = np.ascontiguousarray(samples2d, dtype=np.float32)
         assert x.ndim == 2
@@ -107,6 +116,19 @@ class Ref:
     @staticmethod
     def available() -> bool:
         return os.path.exists(REF_SO)
+
+    def aggregate(self, samples, num_values: int) -> np.ndarray:
+        """`encode aggregate num_values=k` through the reference's own Aggregate()."""
+        if not hasattr(self.lib, "ref_aggregate"):
+            raise RuntimeError("oracle/_ref/libdcref.so predates ref_aggregate: rebuild it where /root/reference exists")
+        self.lib.ref_aggregate.restype = C.c_longlong
+        self.lib.ref_aggregate.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_void_p, C.c_ulonglong]
+        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        out = np.empty((x.size + num_values - 1) // num_values + 1, dtype=np.float32)
+        n = int(self.lib.ref_aggregate(x.ctypes.data if x.size else None, x.size, int(num_values), out.ctypes.data, out.size))
+        if n < 0:
+            raise RuntimeError(f"reference aggregate failed: {n}")
+        return out[:n].copy()
 
     def run_chain(self, stages, data, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
         src = _as_u8(data)

@@ -940,6 +940,23 @@ int dco_dega_decode(const uint8_t *in, uint64_t in_bits, unsigned vs, float nf, 
   return ret;
 }
 
+/* aggregate.c:9-27.  The outer loop runs while input remains (aggregate.c:11); each pass starts a sum at 0
+   (aggregate.c:13), adds up to num_values values in order (aggregate.c:16-20) and stops early when the input
+   ends (aggregate.c:21-22).  volatile keeps the adds separately rounded and in order whatever the flags. */
+uint64_t dco_aggregate(const float *in, uint64_t n, unsigned num_values, float *out)
+{
+  uint64_t i = 0, g = 0;
+  while (i < n)
+  {
+    volatile float sum = 0.0f;
+    unsigned k;
+    for (k = 0; k < num_values && i < n; k++, i++)
+      sum = sum + in[i];
+    out[g++] = sum;
+  }
+  return g;
+}
+
 int64_t dco_dega_encode_batch(const float *samples, uint64_t nstreams, uint64_t len,
                               unsigned vs, float nf, int adaptive)
 {

@@ -80,6 +80,10 @@ int dco_dega_decode(const uint8_t *in, uint64_t in_bits, unsigned vs, float nf, 
 
 /* Batch helper for the CPU baseline: encodes `nstreams` uniform streams of `len` samples one after
    another (single thread, like one DCCLI process per stream) and returns the total payload bytes. */
+/* aggregate.c:9-27 (`encode aggregate num_values=k`) on n float32 values: writes ceil(n / k) sums to out (sequential
+   float32 adds from 0.0f, last group may be short) and returns that count. */
+uint64_t dco_aggregate(const float *in, uint64_t n, unsigned num_values, float *out);
+
 int64_t dco_dega_encode_batch(const float *samples, uint64_t nstreams, uint64_t len,
                               unsigned vs, float nf, int adaptive);
 

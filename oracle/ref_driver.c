@@ -155,3 +155,49 @@ long long ref_run_chain(const char *const *names, const int *encode, int nstages
   mem_bits_close(&b);
   return ret;
 }
+
+/* `encode aggregate num_values=k` (DCLib/src/aggregate.c:9-27) on n float32 values through the real codec.
+   Returns the number of sums written to out (capacity out_cap floats) or a negative error code. */
+long long ref_aggregate(const float *in, unsigned long long n, unsigned num_values, float *out, unsigned long long out_cap)
+{
+  mem_bits a, b;
+  options_t opt;
+  const enc_dec_t *ed = GetEncoder("aggregate");
+  io_int_t ret;
+  unsigned long long got_total = 0;
+  a.fb = b.fb = NULL;
+  a.bb = b.bb = NULL;
+  if (ed == NULL || ed->encoder == NULL)
+    return ERROR_INVALID_VALUE;
+  if (mem_bits_open(&a, FBM_WRITING) != NO_ERROR || mem_bits_open(&b, FBM_WRITING) != NO_ERROR)
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_INIT;
+  }
+  if (n > 0 && WriteBitFileBuffer(a.bb, (const unsigned char *)in, (size_t)(n * 32)) != (io_int_t)(n * 32))
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_CALL;
+  }
+  SetBitFileBufferMode(a.bb, FBM_READING);
+  memset(&opt, 0, sizeof(opt));
+  SetDefaultOptions(&opt);
+  opt.error_log_file = NULL;
+  opt.encode = 1;
+  opt.encoder_decoder = ed;
+  opt.num_values = num_values;
+  ret = (*ed->encoder)(a.bb, b.bb, &opt);
+  SetBitFileBufferMode(b.bb, FBM_READING);
+  while (ret == NO_ERROR && !EndOfBitFileBuffer(b.bb) && got_total < out_cap)
+  {
+    io_int_t got = ReadBitFileBuffer(b.bb, (unsigned char *)(out + got_total), 32);
+    if (got != 32)
+      break;
+    got_total++;
+  }
+  mem_bits_close(&a);
+  mem_bits_close(&b);
+  return ret != NO_ERROR ? (long long)ret : (long long)got_total;
+}

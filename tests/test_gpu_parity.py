@@ -88,6 +88,57 @@ def test_bac_long_pending_runs(ctx, oracle):
                 assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
 
 
+@pytest.mark.parametrize("adaptive", [0, 1])
+def test_bac_carry_through_stored_words(ctx, oracle, adaptive):
+    """Pending runs of up to 300 bits resolved with and without a carry: the carry has to ripple through the encoder's
+    accumulators and through words it has already stored (CarryWriter / bac_ripple in bac.cuh)."""
+    from conftest import straddling_bits
+    rng = np.random.default_rng(3 + adaptive)
+    for n in (1, 31, 32, 33, 63, 64, 65, 129, 300):
+        for tail in ([], [0], [1, 1, 1], list(rng.integers(0, 2, 40))):
+            for prefix, resolve in (((), "up"), ((), "down"), (tuple(rng.integers(0, 2, int(rng.integers(1, 70)))), None)):
+                bits = straddling_bits(n, tail, adaptive, prefix, resolve)
+                packed = np.packbits(bits)
+                want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=adaptive)
+                got = ctx.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=adaptive)
+                assert got == want, (n, tail, prefix, resolve)
+                back = ctx.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=adaptive)
+                assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
+
+
+def test_bac_groups_that_run_out_of_room_are_redone(ctx, oracle):
+    """After 60000 zeros a one costs ~13 bits: the unrolled 16-symbol groups overflow their 31 / 32 bits of room and are
+    redone symbol by symbol (encoder and decoder); > 20 halvings on the way; balanced stretches keep the symbols
+    trading places (the general, swap-aware group form)."""
+    rng = np.random.default_rng(7)
+    bits = np.concatenate([np.zeros(60000, np.uint8), (rng.random(80000) < 0.5).astype(np.uint8), np.ones(60000, np.uint8),
+                           np.tile(np.array([0, 1], np.uint8), 5000), (rng.random(30000) < 0.02).astype(np.uint8)])
+    packed = np.packbits(bits)
+    for ad in (1, 0):
+        want = oracle.run_chain([ob.BAC_ENC], packed, bits.size, adaptive=ad)
+        got = ctx.stage_run(ob.BAC_ENC, packed, bits.size, adaptive=ad)
+        assert got == want
+        back = ctx.stage_run(ob.BAC_DEC, got[1], got[2], adaptive=ad)
+        assert back[0] == 0 and back[2] == bits.size and back[1] == packed.tobytes()
+
+
+def test_warp_interleaved_scratch_with_ragged_stream_counts(ctx, oracle):
+    """Stream counts that are not multiples of 32 (partial warps in the interleaved SEG scratch) and streams of very
+    different lengths inside one warp."""
+    import torch
+    rng = np.random.default_rng(21)
+    for nc, cl, bl in ((1, 37, 0), (3, 100, 7), (33, 65, 0), (5, 1000, 33)):
+        k = np.abs(np.cumsum(rng.integers(-3000, 3001, (nc, cl)), axis=1) + 50000)
+        x = (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+        enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=bl)
+        assert not enc.status.any().item()
+        for s_, xs in enumerate(split_streams(x, bl)):
+            rc, want, nb = oracle.dega_encode(xs)
+            assert rc == 0 and nb == int(enc.bit_len[s_]) and enc.stream_bytes(s_) == want, (nc, cl, bl, s_)
+        y, n_out, status = ctx.dega_decode(enc)
+        assert not status.any().item() and np.array_equal(y.cpu().numpy().view(np.uint32), x.view(np.uint32))
+
+
 def test_garbage_and_truncated_inputs(ctx, oracle):
     rng = np.random.default_rng(9)
     junk = rng.integers(0, 256, 300, dtype=np.uint8)
@@ -307,3 +358,33 @@ def test_full_size_round_trip_and_spot_checks(ctx, oracle):
     assert enc2.stream_bytes(5) == want and int(enc2.bit_len[5]) == nb
     y2, _, _ = ctx.dega_decode(enc2)
     assert torch.equal(y2.view(torch.int32), x[:64].view(torch.int32))
+
+
+# ---- aggregate (granularity reduction) ------------------------------------------------------------
+def test_aggregate_matches_oracle(ctx, oracle):
+    """dc_aggregate_device against the oracle (which is pinned to the reference's Aggregate() by
+    tests/test_oracle_vs_ref.py): bit-exact float32 sums in the reference's order, per channel, short last group."""
+    rng = np.random.default_rng(12)
+    for nc, cl in ((1, 1), (3, 61), (7, 900), (2, 86400)):
+        x = (rng.integers(0, 1 << 20, (nc, cl)).astype(np.float32) / np.float32(100.0)).astype(np.float32)
+        x[rng.random((nc, cl)) < 0.05] *= np.float32(-1e-3)
+        for k in (1, 2, 60, 900, 100000):
+            got = ctx.aggregate(torch.from_numpy(x).cuda(), k).cpu().numpy()
+            assert got.shape == (nc, (cl + k - 1) // k)
+            for c in range(nc):
+                want = oracle.aggregate(x[c], k)
+                assert np.array_equal(got[c].view(np.uint32), want.view(np.uint32)), (nc, cl, k, c)
+
+
+def test_aggregate_then_dega_on_coarser_granularity(ctx, oracle):
+    """1 s -> 1 min on the device, then DEGA on the coarser series: same bytes as the oracle on the aggregated data."""
+    from data_compressor_b200 import synth
+    x = synth.redd_like(8, 7200, device="cuda")
+    xm = ctx.aggregate(x, 60)
+    # sums of sixty two-decimal values are not two-decimal floats any more; normalize with 1.0 like a Wh series
+    enc = ctx.dega_encode(xm, block_len=0, nf=1.0)
+    assert not enc.status.any().item()
+    xs = xm.cpu().numpy()
+    for c in range(8):
+        rc, want, nb = oracle.dega_encode(xs[c], nf=1.0)
+        assert rc == 0 and nb == int(enc.bit_len[c]) and enc.stream_bytes(c) == want

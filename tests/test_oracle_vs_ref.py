@@ -81,3 +81,14 @@ def test_lzmh_random(oracle, ref, seed):
     b = ref.run_chain([ob.LZMH_ENC], data, data.size * 8)
     assert a == b
     assert oracle.run_chain([ob.LZMH_DEC], a[1], a[2]) == ref.run_chain([ob.LZMH_DEC], a[1], a[2])
+
+
+def test_aggregate_oracle_vs_reference(oracle, ref):
+    """`encode aggregate num_values=k` (aggregate.c:9-27): sequential float32 sums, short last group, empty input."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 3, 59, 60, 61, 900, 4097):
+        for k in (1, 2, 3, 15, 60, 900):
+            x = (rng.integers(0, 1 << 20, n).astype(np.float32) / np.float32(100.0)).astype(np.float32)
+            x[rng.random(n) < 0.05] *= np.float32(-1e-3)      # mixed signs and magnitudes: the order of the adds matters
+            a, b = oracle.aggregate(x, k), ref.aggregate(x, k)
+            assert a.size == (n + k - 1) // k and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n, k)
