@@ -45,6 +45,15 @@ class Params(C.Structure):
                 ("adaptive", C.c_int32), ("reserved", C.c_uint32)]
 
 
+class ContainerHeader(C.Structure):
+    """dc_container_header (include/dc_cuda.h): 128 bytes, little endian."""
+    _fields_ = [("magic", C.c_char * 8), ("version", C.c_uint32), ("chain", C.c_uint32), ("value_size_bits", C.c_uint32),
+                ("normalization_factor", C.c_float), ("adaptive", C.c_int32), ("reserved0", C.c_uint32),
+                ("n_channels", C.c_uint64), ("channel_len", C.c_uint64), ("block_len", C.c_uint64), ("n_streams", C.c_uint64),
+                ("payload_bytes", C.c_uint64), ("index_offset", C.c_uint64), ("payload_offset", C.c_uint64),
+                ("reserved", C.c_uint64 * 5)]
+
+
 class Layout(C.Structure):
     """dc_layout: where the streams live inside one flat, channel-major sample array."""
     _fields_ = [("n_channels", C.c_uint64), ("channel_len", C.c_uint64), ("block_len", C.c_uint64),
@@ -55,6 +64,7 @@ class Layout(C.Structure):
 _P, _U64, _I = C.c_void_p, C.c_uint64, C.c_int
 _PL, _PP = C.POINTER(Layout), C.POINTER(Params)
 _PU64 = C.POINTER(C.c_uint64)
+_PH = C.POINTER(ContainerHeader)
 SYMBOLS = {
     "dc_abi_version": (_I, []),
     "dc_create": (_I, [C.POINTER(C.c_void_p), _I]),
@@ -75,6 +85,12 @@ SYMBOLS = {
     "dc_lzmh_encode_device": (_I, [_P, _P, _P, _U64, _P, _U64, _P, _P, _P, _PU64]),
     "dc_lzmh_decode_device": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _P, _P, _P]),
     "dc_aggregate_device": (_I, [_P, _P, _U64, _U64, C.c_uint32, _P]),
+    "dc_container_init_header": (_I, [_PH, C.c_uint32, _PP, _PL, _U64, _U64]),
+    "dc_container_create": (_I, [C.c_char_p, _PH]),
+    "dc_container_write_shard": (_I, [C.c_char_p, _PH, _U64, _U64, _P, _U64, _P, _U64]),
+    "dc_container_read_header": (_I, [C.c_char_p, _PH]),
+    "dc_container_read_index": (_I, [C.c_char_p, _PH, _U64, _U64, _P]),
+    "dc_container_read_payload": (_I, [C.c_char_p, _PH, _U64, _U64, _P]),
     "dc_stage_run_host": (_I, [_P, _I, _P, _U64, _PP, _P, _U64, _PU64]),
     "dc_stage_out_bound": (_U64, [_I, _U64, _PP]),
 }

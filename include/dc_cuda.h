@@ -171,6 +171,49 @@ int dc_lzmh_decode_device(dc_ctx *ctx, const uint8_t *d_payload, uint64_t payloa
 int dc_aggregate_device(dc_ctx *ctx, const float *d_samples, uint64_t n_channels, uint64_t channel_len,
                         uint32_t num_values, float *d_out);
 
+/* ---- container: one file for the streams of a batch encode (host code, no GPU needed) ------- */
+
+/* The reference writes one stream per file (DCIOLib/src/bit_file_buffer.c:310-333 via DCCLI/src/cli.c:129-148).
+   The container keeps every stream's bytes exactly as DCCLI would have written them, back to back, behind a
+   header and a bit-length index; see data_compressor_b200/csrc/container.cpp for the layout. */
+#define DC_CONTAINER_VERSION 1
+#define DC_CHAIN_DEGA 1   /* normalize # diff # seg # bac */
+#define DC_CHAIN_AXDR 2   /* normalize */
+#define DC_CHAIN_LZMH 3   /* lzmh */
+
+typedef struct dc_container_header
+{
+  char     magic[8];              /* "DCB200\0\1" */
+  uint32_t version;
+  uint32_t chain;                 /* DC_CHAIN_* */
+  uint32_t value_size_bits;       /* the stage options the streams were coded with (enc_dec.h:28-41) */
+  float    normalization_factor;
+  int32_t  adaptive;
+  uint32_t reserved0;
+  uint64_t n_channels;            /* dc_layout of the samples (uniform mode); 0 for LZMH byte blocks */
+  uint64_t channel_len;
+  uint64_t block_len;
+  uint64_t n_streams;
+  uint64_t payload_bytes;
+  uint64_t index_offset;          /* file offset of bit_len[n_streams], uint64 little endian */
+  uint64_t payload_offset;        /* file offset of the first stream */
+  uint64_t reserved[5];
+} dc_container_header;            /* 128 bytes */
+
+/* Fills a header (offsets included) for n_streams streams and payload_bytes bytes of payload. */
+int dc_container_init_header(dc_container_header *h, uint32_t chain, const dc_params *params, const dc_layout *layout,
+                             uint64_t n_streams, uint64_t payload_bytes);
+/* Creates / truncates the file, writes the header and sizes the file for index and payload. */
+int dc_container_create(const char *path, const dc_container_header *h);
+/* Writes the index entries [first_stream, first_stream + n) and payload_bytes bytes of payload at byte_base
+   (offsets relative to the container's payload).  Position based: the shards of a multi-GPU job
+   write their own slices, in any order, after one of them has created the file. */
+int dc_container_write_shard(const char *path, const dc_container_header *h, uint64_t first_stream, uint64_t n,
+                             const uint64_t *bit_len, uint64_t byte_base, const uint8_t *payload, uint64_t payload_bytes);
+int dc_container_read_header(const char *path, dc_container_header *h);
+int dc_container_read_index(const char *path, const dc_container_header *h, uint64_t first_stream, uint64_t n, uint64_t *bit_len);
+int dc_container_read_payload(const char *path, const dc_container_header *h, uint64_t byte_off, uint64_t nbytes, uint8_t *dst);
+
 /* ---- plugin face: one stage, one stream, host buffers -------------------------------------- */
 /* What an enc_dec_function_t body (DCLib/inc/enc_dec.h:11) calls after draining its input bit
    buffer: runs ONE reference stage on the GPU over `in_bits` bits and returns the exact output bit

@@ -388,3 +388,22 @@ def test_aggregate_then_dega_on_coarser_granularity(ctx, oracle):
     for c in range(8):
         rc, want, nb = oracle.dega_encode(xs[c], nf=1.0)
         assert rc == 0 and nb == int(enc.bit_len[c]) and enc.stream_bytes(c) == want
+
+
+# ---- container -------------------------------------------------------------------------------------
+def test_container_from_gpu_encode_round_trips(ctx, oracle, tmp_path):
+    from data_compressor_b200 import container as ct
+    rng = np.random.default_rng(31)
+    x = profile(rng, (9, 3000))
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=1000)
+    path = str(tmp_path / "gpu.dcb")
+    h = ct.write_encoded(path, enc)
+    assert (h.n_channels, h.channel_len, h.block_len, h.n_streams, h.payload_bytes) == (9, 3000, 1000, 27, enc.total_bytes)
+    for s in (0, 13, 26):                                   # a stream cut out of the file is what the oracle / DCCLI writes
+        data, nb = ct.stream_file(path, s)
+        c, b = divmod(s, 3)
+        rc, want, wb = oracle.dega_encode(x[c, b * 1000:(b + 1) * 1000])
+        assert rc == 0 and (data, nb) == (want, wb)
+    enc2, h2 = ct.load_encoded(path, "cuda")
+    y, n_out, status = ctx.dega_decode(enc2, vs=h2.value_size_bits, nf=h2.normalization_factor, adaptive=bool(h2.adaptive))
+    assert not status.any().item() and np.array_equal(y.cpu().numpy().view(np.uint32), x.view(np.uint32))

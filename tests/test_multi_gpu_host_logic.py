@@ -20,7 +20,7 @@ def test_channel_ranges_cover_everything():
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
 
 
-def _worker(rank, world, port, n_channels, block_len, q):
+def _worker(rank, world, port, n_channels, block_len, q, container_path=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -29,22 +29,33 @@ def _worker(rank, world, port, n_channels, block_len, q):
     oracle = binding.Oracle()
     x = synth.redd_like(n_channels, 600, device="cpu").numpy()
     lo, hi = shard.channel_range(n_channels, rank, world)
-    payload, sizes = bytearray(), []
+    payload, sizes, bits = bytearray(), [], []
     for c in range(lo, hi):
         for b in range(0, 600, block_len):
             rc, p, nb = oracle.dega_encode(x[c, b:b + block_len])
             assert rc == 0
             payload += p
             sizes.append(len(p))
+            bits.append(nb)
     local_off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64)
     info = shard.exchange_sizes(len(payload), len(sizes), torch.device("cpu"))
     goff = shard.global_byte_offsets(local_off, info["byte_base"])
+    if container_path is not None:
+        # every rank writes its own slice of ONE file: rank 0 creates it, a barrier, then position-based writes
+        from data_compressor_b200 import container as ct
+        bpc = (600 + block_len - 1) // block_len
+        h = ct.make_header(ct.CHAIN_DEGA, info["total_streams"], info["total_bytes"], info["total_streams"] // bpc, 600, block_len)
+        if rank == 0:
+            ct.create(container_path, h)
+        dist.barrier()
+        ct.write_shard(container_path, h, info["stream_base"], np.array(bits, dtype=np.uint64), info["byte_base"],
+                       np.frombuffer(bytes(payload), dtype=np.uint8))
     q.put((rank, bytes(payload), goff.tolist(), info))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_container_layout_matches_single_rank():
+def test_two_rank_container_layout_matches_single_rank(tmp_path):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -52,7 +63,8 @@ def test_two_rank_container_layout_matches_single_rank():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     n_channels, block_len, world = 5, 256, 2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_channels, block_len, q)) for r in range(world)]
+    path = str(tmp_path / "two_ranks.dcb")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_channels, block_len, q, path)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)])
@@ -78,3 +90,11 @@ def test_two_rank_container_layout_matches_single_rank():
         all_offs += goff[:-1]
     assert bytes(container) == bytes(whole)
     assert all_offs + [len(whole)] == offs
+    # the file the two ranks wrote together holds the single-rank layout, stream by stream
+    from data_compressor_b200 import container as ct
+    h = ct.read_header(path)
+    assert (h.n_channels, h.n_streams, h.payload_bytes) == (n_channels, len(offs) - 1, len(whole))
+    assert ct.read_payload(path).tobytes() == bytes(whole)
+    assert ct.byte_offsets(ct.read_index(path)).tolist() == offs
+    rc, y = oracle.dega_decode(*ct.stream_file(path, 7))
+    assert rc == 0 and np.array_equal(y.view(np.uint32), x[7 // 3, (7 % 3) * block_len:(7 % 3 + 1) * block_len].view(np.uint32))
