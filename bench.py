@@ -437,6 +437,55 @@ def run_secondary(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: granularity sweep (1 s / 1 min / 15 min) with block-size and value-size variations.
+# One JSON line per point (kernel-pipeline times, same rules as the headline line); the coarser series are derived
+# on the device with dc_aggregate_device (sums of 60 / 900 one-second samples, turned into mean power and re-quantised to
+# two decimals so that the reference round trip stays bit-exact: sums themselves leave float32's exact range).
+def run_sweep(args):
+    import torch
+    from data_compressor_b200 import Context, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: data_compressor_b200 has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    ctx = Context(0)
+    ctx.set_profiling(True)
+    steps, warm = max(1, min(args.steps, 5)), 2
+    x1 = synth.redd_like(args.channels, SAMPLES, device=dev)
+    hundred = torch.tensor(100.0, dtype=torch.float32, device=dev)
+    series = {"1s": x1}
+    for name, k in (("1min", 60), ("15min", 900)):
+        a = ctx.aggregate(x1, k) / float(k)                                   # mean power of the interval
+        series[name] = (torch.round(a * hundred) / hundred).contiguous()     # two decimals again: exact reference round trip
+    for gran, x in series.items():
+        n = x.shape[1]
+        for vs in (17, 24, 32, 64):
+            if float(x.max().item()) * 100.0 + 0.5 > float(2 ** (vs - 1) - 1):
+                continue      # normalize.c:21-22 would reject the series at this value size
+            for bl in (0, 16384, 4096, 1024):
+                if bl >= n and bl != 0:
+                    continue
+                t_enc = t_dec = 0.0
+                enc = None
+                for it in range(warm + steps):
+                    enc = ctx.dega_encode(x, block_len=bl, vs=vs, nf=NF, adaptive=ADAPTIVE, out=enc)
+                    k1 = ctx.kernel_ms()
+                    y, n_out, status = ctx.dega_decode(enc, vs=vs, nf=NF, adaptive=ADAPTIVE)
+                    k2 = ctx.kernel_ms()
+                    if it >= warm:
+                        t_enc += sum(k1[k] for k in ("front", "bac_encode", "scan", "gather"))
+                        t_dec += sum(k2[k] for k in ("bac_decode", "back"))
+                ok = bool(torch.equal(y.view(torch.int32), x.view(torch.int32))) and not bool(enc.status.any().item())
+                raw = x.numel() * 4
+                enc_ms, dec_ms = t_enc / steps, t_dec / steps
+                print(json.dumps({
+                    "metric": "DEGA encode / decode GB/s of raw samples (configs[4] sweep)", "granularity": gran, "samples_per_channel": n,
+                    "channels": args.channels, "valuesize": vs, "block_len": bl, "streams": enc.n_streams, "encode_ms": enc_ms,
+                    "decode_ms": dec_ms, "encode_gbs": raw / (enc_ms * 1e-3) / 1e9, "decode_gbs": raw / (dec_ms * 1e-3) / 1e9,
+                    "compression_ratio": raw / enc.total_bytes, "round_trip_ok": ok, "n_gpus": 1, "steps": steps, "data": "synthetic"}), flush=True)
+                del y
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,13 +499,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="dega", choices=["dega", "axdr", "lzmh"], help="dega = the contract line; axdr/lzmh = secondary paths")
+    ap.add_argument("--workload", default="dega", choices=["dega", "axdr", "lzmh", "sweep"], help="dega = the contract line; axdr/lzmh = secondary paths; sweep = configs[4]")
     ap.add_argument("--meters", type=int, default=1_000_000)
     ap.add_argument("--valuesize", type=int, default=32)
-    ap.add_argument("--blocks", type=int, default=4096)
+    ap.add_argument("--blocks", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     elif args.workload != "dega":
         run_secondary(args)
     else:

@@ -122,6 +122,13 @@ class Context:
         torch.cuda.current_stream(dev).synchronize()
         rc = fn(self.h, samples.data_ptr(), C.byref(lay), C.byref(par), payload.data_ptr(), int(payload_cap),
                 bit_len.data_ptr(), byte_off.data_ptr(), status.data_ptr(), C.byref(total))
+        if rc == _lib.ERR_MEMORY and total.value > payload_cap:
+            # the library reports the size it needed (series that DEGA expands, e.g. coarse granularities with large
+            # deltas): allocate exactly that and run once more
+            payload_cap = int(total.value)
+            payload = torch.empty(payload_cap + 16, dtype=torch.uint8, device=dev)
+            rc = fn(self.h, samples.data_ptr(), C.byref(lay), C.byref(par), payload.data_ptr(), payload_cap,
+                    bit_len.data_ptr(), byte_off.data_ptr(), status.data_ptr(), C.byref(total))
         self._check(rc, what)
         return Encoded(payload, bit_len, byte_off, status, int(total.value), n_channels, channel_len, int(block_len))
 
