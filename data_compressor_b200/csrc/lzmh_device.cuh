@@ -69,6 +69,14 @@ __device__ __forceinline__ void lz_token(int k, int off, int len, uint32_t &code
 // ---------------------------------------------------------------------------------------------------------
 // Encoder, one warp per stream.  `win` is this warp's shared-memory window, `lsym`/`lcnt` its rank list.
 static const int kLzWin = 1024;   // bytes of the stream kept in shared memory per warp
+static const int kLzWinPad = 16;  // readable slack behind the window (word-wise match compare)
+
+// four bytes starting at byte `idx` of a 4-byte aligned shared-memory array, first byte in the low bits
+__device__ __forceinline__ uint32_t lz_load32(const uint8_t *base, uint32_t idx)
+{
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (idx >> 2);
+  return __funnelshift_r(w[0], w[1], (idx & 3) * 8);
+}
 
 __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uint8_t *win, uint8_t *lsym, uint32_t *lcnt)
 {
@@ -109,9 +117,20 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
         const int off = (int)lane + 1 + 32 * j;
         if (off <= maxoff && win[p - off] == c0)
         {
-          int len = 1;
-          while (len < maxlen && win[p - off + len] == win[p + len])
-            len++;
+          // match length, four bytes per step: unaligned 32-bit reads assembled from aligned words (the window has
+          // slack behind it; whatever is read past maxlen is cut off below)
+          int len = 0;
+          while (len < maxlen)
+          {
+            const uint32_t x = lz_load32(win, p - off + len) ^ lz_load32(win, p + len);
+            if (x != 0)
+            {
+              len += (__ffs((int)x) - 1) >> 3;
+              break;
+            }
+            len += 4;
+          }
+          len = len < maxlen ? len : maxlen;
           const uint32_t k2 = ((uint32_t)len << 8) | (uint32_t)(255 - off);
           if (len >= 3 && k2 > key)
             key = k2;

@@ -13,7 +13,7 @@ static const int kLzEncWarps = 8;
 
 __global__ void __launch_bounds__(kLzEncWarps * 32) lzmh_encode_kernel(const LzmhArgs a)
 {
-  __shared__ __align__(16) uint8_t win[kLzEncWarps][kLzWin];
+  __shared__ __align__(16) uint8_t win[kLzEncWarps][kLzWin + kLzWinPad];
   __shared__ uint8_t lsym[kLzEncWarps][kLzList];
   __shared__ uint32_t lcnt[kLzEncWarps][kLzList];
   const int wid = threadIdx.x >> 5;
