@@ -408,7 +408,11 @@ static void launch_bac(K kernel, const BacArgs &a, cudaStream_t st)
     return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bac_smem_bytes());
   cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
-  kernel<<<resident_grid(a.n_streams, kBacThreads, 1), kBacThreads, bac_smem_bytes(), st>>>(a);
+  // one CTA per SM as soon as there are that many warp tasks: with few streams every SM gets a few warps (which then
+  // run several times faster than in a full SM) instead of a few SMs getting 32 each
+  const uint64_t n_tasks = (a.n_streams + 31) / 32;
+  const unsigned grid = (unsigned)(n_tasks < (uint64_t)sm_count() ? n_tasks : (uint64_t)sm_count());
+  kernel<<<grid, kBacThreads, bac_smem_bytes(), st>>>(a);
   g_launches++;
 }
 
