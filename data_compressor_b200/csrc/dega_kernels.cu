@@ -304,6 +304,109 @@ __global__ void __launch_bounds__(256) axdr_decode_kernel(const AxdrArgs a)
   }
 }
 
+// ---- A-XDR, value size 32: one sample = one word.  Pure streaming (4 B in, 4 B out per sample), so the kernels are
+// written for instruction economy: 32-bit indices, one 128-bit load and store per thread per trip, the stream index
+// by a multiply-high instead of a 64-bit division, index arrays written by the thread that holds a stream's first word.
+struct Magic32
+{
+  uint32_t mul, shift;   // x / d == umulhi(x, mul) >> shift for every 32-bit x (d >= 2; round-up reciprocal with a 33rd bit folded below)
+  uint32_t add;          // 1 when the 33-bit form is needed: q = (((x - t) >> 1) + t) >> (shift - 1), t = umulhi(x, mul)
+};
+
+static Magic32 make_magic32(uint32_t d)
+{
+  // Granlund-Montgomery: l = ceil(log2 d), m = floor(2^32 * (2^l - d) / d) + 1, q = (t + ((x - t) >> 1)) >> (l - 1)
+  Magic32 g;
+  uint32_t l = 0;
+  while ((1ull << l) < d)
+    l++;
+  g.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  g.shift = l;
+  g.add = 1;
+  return g;
+}
+
+__device__ __forceinline__ uint32_t div_magic32(uint32_t x, const Magic32 g)
+{
+  const uint32_t t = __umulhi(x, g.mul);
+  return (t + ((x - t) >> 1)) >> (g.shift - 1);
+}
+
+// normalize.c:16-23 for value size 32; returns false when the range check fails
+__device__ __forceinline__ bool normalize32(float v, float nf, uint32_t &n)
+{
+  if (v > 0.0f)
+    v = __fadd_rn(__fmul_rn(v, nf), 0.5f);
+  else if (v < 0.0f)
+    v = __fsub_rn(__fmul_rn(v, nf), 0.5f);
+  // -(float)2^31 <= v <= (float)(2^31 - 1) == 2^31 (normalize.c:21-22); NaN fails
+  const bool ok = v >= -2147483648.0f && v <= 2147483648.0f;
+  n = v >= 2147483648.0f ? 0x80000000u : (uint32_t)__float2int_rz(v);   // low 32 bits of the int64 truncation
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) axdr_encode32_kernel(const AxdrArgs a, const Magic32 by_wps, const uint32_t total_quads)
+{
+  const uint32_t wps = (uint32_t)a.words_per_stream;
+  const float4 *in = reinterpret_cast<const float4 *>(a.samples_in);
+  uint4 *out = reinterpret_cast<uint4 *>(a.payload_words);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += gridDim.x * blockDim.x)
+  {
+    const float4 v = __ldg(in + q);
+    uint32_t n0, n1, n2, n3;
+    const bool ok0 = normalize32(v.x, a.nf, n0), ok1 = normalize32(v.y, a.nf, n1);
+    const bool ok2 = normalize32(v.z, a.nf, n2), ok3 = normalize32(v.w, a.nf, n3);
+    out[q] = make_uint4(bswap32(n0), bswap32(n1), bswap32(n2), bswap32(n3));
+    const uint32_t g = q * 4;
+    const uint32_t s = div_magic32(g, by_wps);
+    const uint32_t wi = g - s * wps;
+    // a stream starts inside this quad at most once (wps >= 4): word 0 of s, or word (wps - wi) of s + 1
+    if (wi == 0 || wps - wi < 4)
+    {
+      const uint32_t t = wi == 0 ? s : s + 1;
+      a.bit_len[t] = (uint64_t)wps * 32;
+      a.byte_off[t] = (uint64_t)t * wps * 4;
+    }
+    if (!(ok0 && ok1 && ok2 && ok3))   // rare: remember which stream, the caller redoes the batch on the general path
+    {
+      const bool okj[4] = { ok0, ok1, ok2, ok3 };
+      for (uint32_t j = 0; j < 4; j++)
+        if (!okj[j])
+          a.status[(g + j) / wps] = DC_ERR_INVALID_VALUE_D;
+      atomicExch(a.err_flag, 1ull);
+    }
+    if (q == 0)
+      a.byte_off[a.n_streams] = (uint64_t)total_quads * 16;
+  }
+}
+
+__global__ void __launch_bounds__(256) axdr_decode32_kernel(const AxdrArgs a, const Magic32 by_len, const uint32_t total_quads)
+{
+  const uint32_t len = (uint32_t)a.len;
+  const uint4 *in = reinterpret_cast<const uint4 *>(a.payload);
+  float4 *out = reinterpret_cast<float4 *>(a.samples_out);
+  const float nf = a.nf;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += gridDim.x * blockDim.x)
+  {
+    const uint4 w = __ldg(in + q);
+    float4 f;   // normalize.c:36-39: sign-extended value as float32, IEEE division
+    f.x = __fdiv_rn(__int2float_rn((int32_t)bswap32(w.x)), nf);
+    f.y = __fdiv_rn(__int2float_rn((int32_t)bswap32(w.y)), nf);
+    f.z = __fdiv_rn(__int2float_rn((int32_t)bswap32(w.z)), nf);
+    f.w = __fdiv_rn(__int2float_rn((int32_t)bswap32(w.w)), nf);
+    out[q] = f;
+    const uint32_t g = q * 4;
+    const uint32_t s = div_magic32(g, by_len);
+    const uint32_t i = g - s * len;
+    if (i == 0 || len - i < 4)
+    {
+      const uint32_t t = i == 0 ? s : s + 1;
+      a.n_out[t] = len;
+      a.status[t] = 0;
+    }
+  }
+}
+
 void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
 {
   const uint64_t total = (a.n_streams * a.words_per_stream + 3) / 4;
@@ -312,7 +415,11 @@ void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
   const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);   // grid-stride over a multiple of the SM count
-  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0)
+  const uint64_t total_words = a.n_streams * a.words_per_stream;
+  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.payload_words) & 15) == 0 &&
+      a.words_per_stream >= 4 && total_words % 4 == 0 && total_words < (1ull << 32))
+    axdr_encode32_kernel<<<grid, block, 0, st>>>(a, make_magic32((uint32_t)a.words_per_stream), (uint32_t)(total_words / 4));
+  else if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0)
     axdr_encode_kernel<true><<<grid, block, 0, st>>>(a);
   else
     axdr_encode_kernel<false><<<grid, block, 0, st>>>(a);
@@ -327,7 +434,12 @@ void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
   const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
-  axdr_decode_kernel<<<grid, block, 0, st>>>(a);
+  const uint64_t total_samples = a.n_streams * a.len;
+  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.payload) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0 &&
+      a.len >= 4 && total_samples % 4 == 0 && total_samples < (1ull << 32))
+    axdr_decode32_kernel<<<grid, block, 0, st>>>(a, make_magic32((uint32_t)a.len), (uint32_t)(total_samples / 4));
+  else
+    axdr_decode_kernel<<<grid, block, 0, st>>>(a);
   g_launches++;
 }
 
