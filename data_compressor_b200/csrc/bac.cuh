@@ -45,25 +45,6 @@ namespace dc {
 
 static const uint32_t kBacMaxFreq = 0x3FFFu;   // MAX_FREQUENCY, bac.c:27
 
-// PTX shifts clamp the amount to 32 (C++ shifts by >= 32 are undefined)
-#ifdef DC_HOST_SIM
-static inline uint32_t shl_c(uint32_t a, uint32_t n) { return n >= 32 ? 0u : a << n; }
-static inline uint32_t shr_c(uint32_t a, uint32_t n) { return n >= 32 ? 0u : a >> n; }
-#else
-__device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n)
-{
-  uint32_t r;
-  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));
-  return r;
-}
-__device__ __forceinline__ uint32_t shr_c(uint32_t a, uint32_t n)
-{
-  uint32_t r;
-  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));
-  return r;
-}
-#endif
-
 // Count of leading zeros of a NON-ZERO word: bfind.shiftamt is a single FLO.U32.SH (the generic __clz costs FLO + IADD)
 #ifdef DC_HOST_SIM
 static inline uint32_t clz_nz(uint32_t a) { return (uint32_t)__builtin_clz(a); }
