@@ -325,7 +325,7 @@ def run_ours(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dom_ms,
                 "note": "the coder is sequential per stream and bound by integer instruction issue (~1.9 cycles per integer instruction per scheduler, profiles/r1_ubench_pipes.txt; DRAM < 4 %): "
-                        "DESIGN.md 3.1, profiles/r1g_dega_ncu_summary.txt"}
+                        "DESIGN.md 3.1, profiles/r1h_dega_ncu_summary.txt"}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cpu = None
