@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
 #ifndef BACK_MIN_CTAS
 #define BACK_MIN_CTAS 10
 #endif
-template <bool NARROW>
+template <int MODE>
 __global__ void __launch_bounds__(128, BACK_MIN_CTAS) back_dega_kernel(const BackArgs a)
 {
   __shared__ float stage[128 * kBackStage];   // decoded samples per thread, leaving as 128-bit stores of whole sectors
   float *mine = stage + threadIdx.x * kBackStage;
-  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { back_dega_body<NARROW>(a, s, mine); });
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { back_dega_body<MODE>(a, s, mine); });
 }
 
 void launch_back(const BackArgs &a, cudaStream_t st)
@@ -126,10 +126,13 @@ void launch_back(const BackArgs &a, cudaStream_t st)
   {
     cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
     const unsigned rgrid = resident_grid(a.n_streams, block, BACK_MIN_CTAS);
-    if (a.vs <= 32 && a.in.stride_bytes < (1ull << 28))   // every stream shorter than 2^31 bits
-      back_dega_kernel<true><<<rgrid, block, 0, st>>>(a);
+    const bool narrow = a.vs <= 32 && a.in.stride_bytes < (1ull << 28);   // every stream shorter than 2^31 bits
+    if (narrow && a.vs == 32 && a.in.interleave)
+      back_dega_kernel<2><<<rgrid, block, 0, st>>>(a);
+    else if (narrow)
+      back_dega_kernel<1><<<rgrid, block, 0, st>>>(a);
     else
-      back_dega_kernel<false><<<rgrid, block, 0, st>>>(a);
+      back_dega_kernel<0><<<rgrid, block, 0, st>>>(a);
   }
   else
     back_kernel<<<grid, block, 0, st>>>(a);

@@ -67,6 +67,7 @@ static inline float __fsub_rn(float a, float b)
   volatile float r = a - b;
   return r;
 }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fdiv_rn(float a, float b)
 {
   volatile float r = a / b;

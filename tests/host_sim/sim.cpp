@@ -183,9 +183,9 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
       {
         float stage4[kBackStage];
         if (ka.vs <= 32)
-          back_dega_body<true>(ka, 0, stage4);
+          back_dega_body<1>(ka, 0, stage4);
         else
-          back_dega_body<false>(ka, 0, stage4);
+          back_dega_body<0>(ka, 0, stage4);
       }
       else
         back_body(ka, 0);
@@ -339,10 +339,12 @@ int sim_dega_decode_batch(const uint8_t *payload, const uint64_t *bit_len, const
     if (vs >= 17)
     {
       float stage4[kBackStage];
-      if (vs <= 32)
-        back_dega_body<true>(ka, s, stage4);
+      if (vs == 32)
+        back_dega_body<2>(ka, s, stage4);     // the decode pipeline's configuration: interleaved scratch, value size 32
+      else if (vs <= 32)
+        back_dega_body<1>(ka, s, stage4);
       else
-        back_dega_body<false>(ka, s, stage4);
+        back_dega_body<0>(ka, s, stage4);
     }
     else
       back_body(ka, s);

@@ -407,3 +407,26 @@ def test_container_from_gpu_encode_round_trips(ctx, oracle, tmp_path):
     enc2, h2 = ct.load_encoded(path, "cuda")
     y, n_out, status = ctx.dega_decode(enc2, vs=h2.value_size_bits, nf=h2.normalization_factor, adaptive=bool(h2.adaptive))
     assert not status.any().item() and np.array_equal(y.cpu().numpy().view(np.uint32), x.view(np.uint32))
+
+
+@pytest.mark.parametrize("nf", [100.0, 1.0, 3.0, 7.3, 0.01, 1000.0, 1e-5, 123456.789])
+def test_denormalize_division_is_ieee_for_any_factor(ctx, oracle, nf):
+    """The back end divides by the normalization factor with a reciprocal hoisted out of the sample loop (NfDivider in
+    dega_device.cuh); the result has to be the correctly rounded float32 quotient the reference's divss gives, for
+    small and large integers and for factors that are not exactly representable."""
+    rng = np.random.default_rng(int(nf * 1000) % 1000 + 5)
+    k = np.concatenate([np.arange(0, 300), rng.integers(0, 1 << 24, 3000), rng.integers(0, (1 << 31) - 300, 3000)]).astype(np.int64)
+    k = np.abs(np.sort(k)[::-1] if nf == 3.0 else k)
+    x = (k.astype(np.float32) / np.float32(nf)).astype(np.float32).reshape(4, -1)
+    x = x[:, : x.shape[1] // 8 * 8]
+    # keep only inputs the reference chain accepts at value size 32 (normalize.c:21-22, diff.c:17-18)
+    v = x.astype(np.float32) * np.float32(nf) + np.float32(0.5)
+    x[v >= np.float32(2147483000.0)] = np.float32(1.0) / np.float32(nf)
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=0, nf=nf)
+    assert not enc.status.any().item()
+    y, n_out, status = ctx.dega_decode(enc, nf=nf)
+    assert not status.any().item()
+    got = y.cpu().numpy()
+    for c in range(x.shape[0]):
+        rc, want = oracle.dega_decode(enc.stream_bytes(c), int(enc.bit_len[c]), nf=nf, out_cap=x.shape[1] * 4 + 64)
+        assert rc == 0 and np.array_equal(got[c].view(np.uint32), want.view(np.uint32)), (nf, c)
