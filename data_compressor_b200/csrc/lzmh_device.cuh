@@ -111,29 +111,40 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
       // ---- match search (lzmh.c:192-214): 4 offsets per lane, ascending, strictly longer wins
       uint32_t key = 0;   // (length << 8) | (255 - offset): max = longest, then smallest offset
       const uint8_t c0 = win[p];
+      const uint32_t w0 = lz_load32(win, p);   // the four bytes at the parse position (same for every lane: a broadcast)
 #pragma unroll
       for (int j = 0; j < 4; j++)
       {
         const int off = (int)lane + 1 + 32 * j;
-        if (off <= maxoff && win[p - off] == c0)
+        if (off <= maxoff)
         {
-          // match length, four bytes per step: unaligned 32-bit reads assembled from aligned words (the window has
-          // slack behind it; whatever is read past maxlen is cut off below)
-          int len = 0;
-          while (len < maxlen)
+          // Only matches of three bytes or more count (lzmh.c:216), so the first test is on three bytes at once and
+          // runs for all lanes in step; the extension loop -- four bytes per trip, unaligned reads assembled from
+          // aligned words, whatever is read past maxlen cut off below -- is left to the few candidates that matched
+          // four bytes already.
+          uint32_t x = lz_load32(win, p - off) ^ w0;
+          if ((x & 0x00FFFFFFu) == 0)
           {
-            const uint32_t x = lz_load32(win, p - off + len) ^ lz_load32(win, p + len);
-            if (x != 0)
+            int len = 3;
+            if (x == 0)
             {
-              len += (__ffs((int)x) - 1) >> 3;
-              break;
+              len = 4;
+              while (len < maxlen)
+              {
+                x = lz_load32(win, p - off + len) ^ lz_load32(win, p + len);
+                if (x != 0)
+                {
+                  len += (__ffs((int)x) - 1) >> 3;
+                  break;
+                }
+                len += 4;
+              }
             }
-            len += 4;
+            len = len < maxlen ? len : maxlen;
+            const uint32_t k2 = ((uint32_t)len << 8) | (uint32_t)(255 - off);
+            if (len >= 3 && k2 > key)
+              key = k2;
           }
-          len = len < maxlen ? len : maxlen;
-          const uint32_t k2 = ((uint32_t)len << 8) | (uint32_t)(255 - off);
-          if (len >= 3 && k2 > key)
-            key = k2;
         }
       }
       key = __reduce_max_sync(0xFFFFFFFFu, key);
