@@ -132,6 +132,29 @@ def cpu_baseline_run(sample_blocks, cores, kind):
     return raw / busy / 1e9, busy, wall
 
 
+def _cpu_worker_stage(args):
+    """Secondary paths: runs one reference chain (list of oracle stage ids) over a list of byte blocks."""
+    kind, chain, blocks, vs, nf = args
+    from oracle import binding
+    impl = binding.Ref() if kind == "reference" else binding.Oracle()
+    t0 = time.perf_counter()
+    for b in blocks:
+        rc, out, nb = impl.run_chain(chain, b, b.size * 8, vs, nf, 0)
+        assert rc == 0
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_stage(chain, blocks, cores, kind, vs=32, nf=100.0):
+    """GB/s of input bytes for `chain` over `blocks` (uint8 arrays) on `cores` worker processes."""
+    import multiprocessing as mp
+    shards = [blocks[i::cores] for i in range(cores)]
+    shards = [s for s in shards if s]
+    with mp.get_context("spawn").Pool(len(shards)) as pool:
+        res = pool.map(_cpu_worker_stage, [(kind, chain, s, vs, nf) for s in shards])
+    busy = max(res)
+    return sum(b.size for b in blocks) / busy / 1e9, busy
+
+
 def cpu_kind():
     from oracle import binding
     return "reference" if binding.Ref.available() else "port"
@@ -411,6 +434,17 @@ def run_secondary(args):
         raw = x.numel() * 4
         alg = raw + enc.total_bytes
         enc_ms, dec_ms = job_ms(t_enc / steps, t_dec / steps)
+        cpu = None
+        if rank == 0 and not args.no_cpu:
+            # the reference's `encode normalize` on a bounded sample of the same meters, all host cores
+            from oracle import binding as ob
+            ob.build(ref=os.path.isdir("/root/reference/DataCompressor"))
+            kind, cores = cpu_kind(), os.cpu_count() or 1
+            per_core = max(1, int(args.cpu_seconds * 15e6 / (n_samples * 4)))          # ~18 MB/s per core
+            xs = x[: per_core * cores].cpu().numpy()
+            gbs, busy = cpu_baseline_stage([ob.NORMALIZE], [row.view("uint8") for row in xs], cores, kind, vs, NF)
+            cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "seconds": busy,
+                   "sample": f"{xs.shape[0]} meters of {n_samples} samples ({xs.nbytes / 1e6:.1f} MB raw), encode normalize, one worker process per core"}
         line = {"metric": "A-XDR (normalize only) encode GB/s of raw samples", "value": world * raw / (enc_ms * 1e-3) / 1e9, "unit": "GB/s",
                 "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": enc_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32->i64", "data": "synthetic",
@@ -420,7 +454,7 @@ def run_secondary(args):
                 "roofline": {"bound": "hbm", "kernel": "axdr_encode_kernel", "achieved": alg / (enc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / (enc_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": int(alg)},
-                "gpu_launches": ctx.launch_count()}
+                "cpu_baseline": cpu, "gpu_launches": ctx.launch_count()}
     else:   # lzmh
         n_blocks, block = args.blocks, 65536
         chans = (n_blocks * block + 2 * 86400 - 1) // (2 * 86400)
@@ -440,6 +474,17 @@ def run_secondary(args):
         ok = bool(torch.equal(out[: raw], data)) if same == n_blocks else None
         enc_ms, dec_ms = job_ms(t_enc / steps, t_dec / steps)
         alg = raw + total
+        cpu = None
+        if rank == 0 and not args.no_cpu:
+            # the reference's `encode lzmh` on a bounded sample of the same blocks, all host cores
+            from oracle import binding as ob
+            ob.build(ref=os.path.isdir("/root/reference/DataCompressor"))
+            kind, cores = cpu_kind(), os.cpu_count() or 1
+            per_core = max(1, int(args.cpu_seconds * 2.5e6 / block))                       # ~2.7 MB/s per core
+            hb = data[: per_core * cores * block].cpu().numpy().reshape(-1, block)
+            gbs, busy = cpu_baseline_stage([ob.LZMH_ENC], [row for row in hb], cores, kind)
+            cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "seconds": busy,
+                   "sample": f"{hb.shape[0]} blocks of {block} bytes ({hb.nbytes / 1e6:.1f} MB), encode lzmh, one worker process per core"}
         line = {"metric": "LZMH encode GB/s of input bytes", "value": world * raw / (enc_ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": enc_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
@@ -450,7 +495,7 @@ def run_secondary(args):
                 "roofline": {"bound": "hbm", "kernel": "lzmh_encode_kernel", "achieved": alg / (enc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / (enc_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": int(alg), "note": "sequential greedy parse per block: issue/latency bound"},
-                "gpu_launches": ctx.launch_count()}
+                "cpu_baseline": cpu, "gpu_launches": ctx.launch_count()}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
