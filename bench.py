@@ -88,6 +88,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "how": "NVML, 100 ms period, during the timed region"}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pins this process to the CPUs NVML reports as local to its GPU, before any pinned host buffer is allocated, so
+    that the staging memory of the end-to-end path sits on the GPU's own NUMA node (eight ranks otherwise share
+    whatever node the kernel picked and the copies cross the socket link).  Plumbing only; silently skipped if NVML
+    or the affinity call is unavailable."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -220,6 +244,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU: data_compressor_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -324,7 +349,8 @@ def run_ours(args):
         meta = n_streams * (8 + 8 + 4) + 8
         e2e = {"value": world * raw_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(raw_bytes + pay.size + meta), "d2h_bytes_per_step": int(raw_bytes + pay.size + 2 * meta),
-               "api": "dc_dega_encode_host + dc_dega_decode_host (include/dc_cuda.h), host buffers, copies inside the timed region"}
+               "api": "dc_dega_encode_host + dc_dega_decode_host (include/dc_cuda.h), host buffers, copies inside the timed region",
+               "host_cpus_bound": numa_cpus}
 
     if rank != 0:
         if world > 1:
