@@ -1281,7 +1281,6 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       fa.out.nbits = stage == DC_STAGE_DEGA_ENC ? d_meta + 1 : d_meta + 2;
       fa.status = d_status;
       fa.work = c->d_work;
-    fa.work = c->d_work;
       launch_front(fa, c->stream);
     }
     if (stage == DC_STAGE_BAC_ENC || stage == DC_STAGE_DEGA_ENC)
@@ -1355,7 +1354,6 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
       ka.n_out = d_meta + 3;
       ka.status = d_status;
       ka.work = c->d_work;
-  ka.work = c->d_work;
       launch_back(ka, c->stream);
     }
     if ((rc = check_launch(c, "stage kernels")) != DC_OK)
