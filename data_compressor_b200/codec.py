@@ -173,6 +173,18 @@ class Context:
     def axdr_decode(self, enc: Encoded, vs: int = 32, nf: float = 100.0, out: torch.Tensor | None = None):
         return self._decode(self.lib.dc_axdr_decode_device, "dc_axdr_decode_device", enc, vs, nf, False, out)
 
+    # ---- csv: text column -> float32 --------------------------------------------------------------
+    def csv_decode(self, text, column: int = 1, separator: str = ",") -> np.ndarray:
+        """`decode csv column=.. separator=..` (DCLib/src/csv.c:13-44): the column's values as float32, in line order."""
+        src = np.frombuffer(text.encode() if isinstance(text, str) else bytes(text), dtype=np.uint8)
+        cap = max(16, int(np.count_nonzero(src == 10)) + 1)
+        out = np.empty(cap, dtype=np.float32)
+        n = C.c_uint64(0)
+        rc = self.lib.dc_csv_decode_host(self.h, src.ctypes.data if src.size else None, src.size, int(column), separator.encode()[:1],
+                                         out.ctypes.data, cap, C.byref(n))
+        self._check(rc, "dc_csv_decode_host")
+        return out[: n.value].copy()
+
     # ---- aggregate: granularity reduction ---------------------------------------------------------
     def aggregate(self, x: torch.Tensor, num_values: int) -> torch.Tensor:
         """`encode aggregate num_values=k` (DCLib/src/aggregate.c:9-27) for every channel of a float32

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/dc_cuda.h"
@@ -760,6 +761,101 @@ int dc_aggregate_device(dc_ctx *c, const float *d_samples, uint64_t n_channels, 
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
   launch_aggregate(d_samples, n_channels, channel_len, num_values, d_out, c->stream);
   return check_launch(c, "aggregate_kernel");
+}
+
+// ---- csv ---------------------------------------------------------------------------------------------------
+int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t column, char separator, float *out, uint64_t out_cap,
+                       uint64_t *n_out)
+{
+  if (!c || column == 0 || (nbytes && !text) || !n_out)
+    return DC_ERR_INVALID_VALUE;
+  *n_out = 0;
+  if (nbytes == 0)
+    return DC_OK;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  c->ev_mask = 0;
+  // phase 1 (staging block): the text and the line ends
+  const uint64_t tiles = csv_tiles(nbytes);
+  const uint64_t scan_tmp = (tiles + 4095) / 4096 + 2;
+  int rc = stage_reserve(c, Bump::size_of(nbytes + 64, 1) + 2 * Bump::size_of(tiles + 1, 8) + Bump::size_of(scan_tmp, 8) + 4096);
+  if (rc != DC_OK)
+    return rc;
+  Bump bs(c->stage);
+  uint8_t *d_text = bs.take<uint8_t>(nbytes + 64);
+  uint64_t *d_tile_bits = bs.take<uint64_t>(tiles + 1);
+  uint64_t *d_tile_off = bs.take<uint64_t>(tiles + 1);
+  uint64_t *d_tmp = bs.take<uint64_t>(scan_tmp);
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);   // the staging block may still be read by an earlier call's copy-back
+  CU_TRY(c, cudaMemcpyAsync(d_text, text, nbytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  launch_csv_count(d_text, nbytes, d_tile_bits, c->stream);
+  launch_byte_scan(d_tile_bits, tiles, d_tile_off, d_tmp, c->stream);
+  if ((rc = check_launch(c, "csv line count")) != DC_OK)
+    return rc;
+  uint64_t n_newlines = 0;
+  if ((rc = read_back(c, d_tile_off + tiles, &n_newlines, 1)) != DC_OK)
+    return rc;
+  const uint64_t n_lines = n_newlines + (text[nbytes - 1] != '\n' ? 1 : 0);   // an unterminated last line counts (csv.c:22)
+  // phase 2 (arena): per-line results
+  const uint64_t hard_cap = n_lines < (1ull << 20) ? n_lines : (1ull << 20);
+  const uint64_t scan_tmp2 = (n_lines + 4095) / 4096 + 2;
+  rc = arena_reserve(c, 5 * Bump::size_of(n_lines + 1, 8) + Bump::size_of(n_lines, 4) + Bump::size_of(out_cap, 4) + Bump::size_of(hard_cap, 8) +
+                            Bump::size_of(scan_tmp2, 8) + Bump::size_of(8, 8) + 4096);
+  if (rc != DC_OK)
+    return rc;
+  Bump ba(c->arena);
+  uint64_t *d_line_end = ba.take<uint64_t>(n_lines + 1);
+  uint64_t *d_flag8 = ba.take<uint64_t>(n_lines + 1);
+  uint64_t *d_pos = ba.take<uint64_t>(n_lines + 1);
+  uint64_t *d_lo = ba.take<uint64_t>(n_lines + 1);
+  uint64_t *d_hi = ba.take<uint64_t>(n_lines + 1);
+  float *d_value = ba.take<float>(n_lines);
+  float *d_out = ba.take<float>(out_cap);
+  uint64_t *d_hard = ba.take<uint64_t>(hard_cap);
+  uint64_t *d_tmp2 = ba.take<uint64_t>(scan_tmp2);
+  unsigned long long *d_nhard = reinterpret_cast<unsigned long long *>(ba.take<uint64_t>(8));
+  CU_TRY(c, cudaMemsetAsync(d_nhard, 0, sizeof(unsigned long long), c->stream), DC_ERR_LIBRARY_CALL);
+  launch_csv_lines(d_text, nbytes, d_tile_off, d_line_end, c->stream);
+  launch_csv_parse(d_text, nbytes, d_line_end, n_newlines, n_lines, column, (uint8_t)separator, d_value, d_flag8, d_lo, d_hi, d_nhard, d_hard,
+                   hard_cap, c->stream);
+  launch_byte_scan(d_flag8, n_lines, d_pos, d_tmp2, c->stream);
+  if ((rc = check_launch(c, "csv parse")) != DC_OK)
+    return rc;
+  uint64_t total = 0, n_hard = 0;
+  if ((rc = read_back(c, d_pos + n_lines, &total, 1)) != DC_OK ||
+      (rc = read_back(c, reinterpret_cast<const uint64_t *>(d_nhard), &n_hard, 1)) != DC_OK)
+    return rc;
+  *n_out = total;
+  if (total > out_cap)
+  {
+    set_err(c, "csv column holds %llu values, capacity is %llu", (unsigned long long)total, (unsigned long long)out_cap);
+    return DC_ERR_MEMORY;
+  }
+  if (n_hard > hard_cap)
+  {
+    set_err(c, "%llu fields need strtof, more than the %llu this call keeps track of", (unsigned long long)n_hard, (unsigned long long)hard_cap);
+    return DC_ERR_INVALID_FORMAT;
+  }
+  launch_csv_compact(d_value, d_flag8, d_pos, n_lines, d_out, out_cap, c->stream);
+  if ((rc = check_launch(c, "csv compact")) != DC_OK)
+    return rc;
+  if (total)
+    CU_TRY(c, cudaMemcpyAsync(out, d_out, total * sizeof(float), cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  // fields outside the fast grammar (exponents, hex floats, inf/nan, long digit strings): strtof itself, like csv.c:31
+  if (n_hard)
+  {
+    std::vector<uint64_t> idx(n_hard), lo(n_hard), hi(n_hard), pos(n_hard);
+    CU_TRY(c, cudaMemcpy(idx.data(), d_hard, n_hard * 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
+    for (uint64_t h = 0; h < n_hard; h++)
+    {
+      CU_TRY(c, cudaMemcpy(&lo[h], d_lo + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpy(&hi[h], d_hi + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpy(&pos[h], d_pos + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
+      std::string field(reinterpret_cast<const char *>(text) + lo[h], hi[h] - lo[h]);
+      out[pos[h]] = strtof(field.c_str(), nullptr);
+    }
+  }
+  return DC_OK;
 }
 
 // ---- DEGA, host buffers ----------------------------------------------------------------------------------

@@ -1,0 +1,236 @@
+// csv_kernels.cu -- `decode csv` (DCLib/src/csv.c:13-44, ReadCSV) on the device: one column of a text file -> float32.
+//
+// ReadCSV walks the text character by character: fields end at the separator, at '\n' or at the end of the input,
+// '\n' resets the column counter, and every time the wanted column ends its text goes through strtof (csv.c:22-35).
+// Lines that do not have the column produce nothing.  Here:
+//   1. csv_count_kernel / csv_lines_kernel: positions of the line ends (per-tile counts, a scan, a ranked scatter);
+//   2. csv_parse_kernel: one thread per line finds the wanted field and converts it;
+//   3. the values of the lines that have the column are compacted in line order (scan over the flags).
+// Conversion: strtof is a correctly rounded decimal -> binary32 conversion.  A field of the form
+// [space]* [+-]? digits [. digits]  whose digits, after dropping leading zeros and trailing fraction zeros, make an
+// integer M < 2^24 with at most ten fraction digits k is converted as float(M) / 10^k: both operands are exact in
+// binary32, so the IEEE division is the correctly rounded result, i.e. strtof's.  Integers without a fraction up to
+// 19 digits go through the correctly rounded integer -> float conversion.  Everything else strtof accepts (exponents,
+// hex floats, inf/nan, more digits) is flagged and converted by the caller with strtof itself; meter readings never
+// get there.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace dc {
+
+void count_launch(int n);
+
+static const int kCsvTile = 4096;      // bytes per CTA
+static const int kCsvThreads = 256;    // 16 bytes per thread
+
+__global__ void __launch_bounds__(kCsvThreads) csv_count_kernel(const uint8_t *text, uint64_t n, uint64_t *tile_bits)
+{
+  __shared__ uint32_t total;
+  if (threadIdx.x == 0)
+    total = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kCsvTile + (uint64_t)threadIdx.x * 16;
+  uint32_t cnt = 0;
+  for (int k = 0; k < 16; k++)
+    if (base + k < n && text[base + k] == '\n')
+      cnt++;
+  cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt)
+    atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    tile_bits[blockIdx.x] = (uint64_t)total * 8;   // launch_byte_scan sums ceil(bits / 8)
+}
+
+// line_end[r] = position of the r-th '\n'; tile_off = exclusive scan of the tile counts
+__global__ void __launch_bounds__(kCsvThreads) csv_lines_kernel(const uint8_t *text, uint64_t n, const uint64_t *tile_off, uint64_t *line_end)
+{
+  __shared__ uint32_t warp_base[kCsvThreads / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * kCsvTile + (uint64_t)threadIdx.x * 16;
+  uint32_t mask = 0;
+  for (int k = 0; k < 16; k++)
+    if (base + k < n && text[base + k] == '\n')
+      mask |= 1u << k;
+  const uint32_t cnt = __popc(mask);
+  uint32_t inc = cnt;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d)
+      inc += t;
+  }
+  if (lane == 31)
+    warp_base[wid] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < wid; w++)
+    before += warp_base[w];
+  uint64_t rank = tile_off[blockIdx.x] + before + inc - cnt;
+  while (mask)
+  {
+    const int k = __ffs((int)mask) - 1;
+    mask &= mask - 1;
+    line_end[rank++] = base + (uint64_t)k;
+  }
+}
+
+__device__ __forceinline__ bool csv_is_space(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+__device__ __forceinline__ bool csv_is_digit(uint8_t c) { return c >= '0' && c <= '9'; }
+
+// value[j], flag8[j] (8 = the line has the column, 0 = it does not), and the indices of fields strtof has to convert
+__global__ void __launch_bounds__(256) csv_parse_kernel(const uint8_t *text, uint64_t n, const uint64_t *line_end, uint64_t n_newlines,
+                                                        uint64_t n_lines, uint32_t column, uint8_t sep, float *value, uint64_t *flag8,
+                                                        uint64_t *field_lo, uint64_t *field_hi, unsigned long long *n_hard,
+                                                        uint64_t *hard_list, uint64_t hard_cap)
+{
+  const float pow10f[11] = { 1.0f, 10.0f, 100.0f, 1000.0f, 10000.0f, 100000.0f, 1000000.0f, 10000000.0f, 100000000.0f, 1000000000.0f, 10000000000.0f };
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_lines; j += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint64_t start = j == 0 ? 0 : line_end[j - 1] + 1;
+    const uint64_t end = j < n_newlines ? line_end[j] : n;   // position of the '\n', or the end of the input
+    // the wanted field: csv.c:22-40, columns are counted from 1
+    uint64_t fs = start, fe = end;
+    uint32_t col = 1;
+    bool have = false;
+    for (uint64_t i = start; i <= end; i++)
+    {
+      if (i == end || text[i] == sep)
+      {
+        if (col == column)
+        {
+          fe = i;
+          // an EMPTY field that ends with the input (unterminated last line ending in a separator) is never seen by
+          // the reference: its loop stops with the last character (csv.c:20)
+          have = !(i == end && end == n && fs == end);
+          break;
+        }
+        col++;
+        fs = i + 1;
+      }
+    }
+    flag8[j] = have ? 8 : 0;
+    field_lo[j] = fs;
+    field_hi[j] = fe;
+    if (!have)
+      continue;
+    // ---- strtof on text[fs, fe)
+    uint64_t i = fs;
+    while (i < fe && csv_is_space(text[i]))
+      i++;
+    bool neg = false;
+    if (i < fe && (text[i] == '+' || text[i] == '-'))
+      neg = text[i++] == '-';
+    const uint64_t num_start = i;
+    uint64_t M = 0;
+    uint32_t sig = 0, k = 0, ndig = 0;
+    bool hard = false, frac = false;
+    for (; i < fe; i++)
+    {
+      const uint8_t c = text[i];
+      if (csv_is_digit(c))
+      {
+        ndig++;
+        if (sig > 0 || c != '0')
+        {
+          if (sig < 19)
+            M = M * 10 + (uint64_t)(c - '0');
+          else
+            hard = true;
+          sig++;
+        }
+        if (frac)
+          k++;
+      }
+      else if (c == '.' && !frac)
+        frac = true;
+      else
+        break;
+    }
+    float f = 0.0f;
+    if (ndig == 0)
+    {
+      // no conversion: strtof returns +0 ... unless the text spells inf / nan
+      if (i < fe && (text[i] == 'i' || text[i] == 'I' || text[i] == 'n' || text[i] == 'N'))
+        hard = true;
+      neg = false;
+    }
+    else
+    {
+      const uint8_t c = i < fe ? text[i] : 0;
+      if (c == 'e' || c == 'E' || c == 'p' || c == 'P')
+        hard = true;                                            // possibly an exponent
+      if ((c == 'x' || c == 'X') && i == num_start + 1 && text[num_start] == '0')
+        hard = true;                                            // hex float
+      while (k > 0 && M != 0 && M % 10 == 0)                    // trailing fraction zeros carry no information
+      {
+        M /= 10;
+        k--;
+        sig--;
+      }
+      if (M == 0)
+        f = 0.0f;
+      else if (k == 0 && sig <= 19)
+        f = __ull2float_rn(M);
+      else if (M < (1ull << 24) && k <= 10)
+        f = __fdiv_rn((float)M, pow10f[k]);
+      else
+        hard = true;
+    }
+    value[j] = neg ? -f : f;
+    if (hard)
+    {
+      const unsigned long long h = atomicAdd(n_hard, 1ull);
+      if (h < hard_cap)
+        hard_list[h] = j;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) csv_compact_kernel(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out,
+                                                          uint64_t out_cap)
+{
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_lines; j += (uint64_t)gridDim.x * blockDim.x)
+    if (flag8[j] && pos[j] < out_cap)
+      out[pos[j]] = value[j];
+}
+
+static unsigned csv_grid(uint64_t n, unsigned block)
+{
+  const uint64_t want = (n + block - 1) / block;
+  return (unsigned)(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16);
+}
+
+void launch_csv_count(const uint8_t *text, uint64_t n, uint64_t *tile_bits, cudaStream_t st)
+{
+  csv_count_kernel<<<(unsigned)((n + kCsvTile - 1) / kCsvTile), kCsvThreads, 0, st>>>(text, n, tile_bits);
+  count_launch(1);
+}
+
+void launch_csv_lines(const uint8_t *text, uint64_t n, const uint64_t *tile_off, uint64_t *line_end, cudaStream_t st)
+{
+  csv_lines_kernel<<<(unsigned)((n + kCsvTile - 1) / kCsvTile), kCsvThreads, 0, st>>>(text, n, tile_off, line_end);
+  count_launch(1);
+}
+
+void launch_csv_parse(const uint8_t *text, uint64_t n, const uint64_t *line_end, uint64_t n_newlines, uint64_t n_lines, uint32_t column, uint8_t sep,
+                      float *value, uint64_t *flag8, uint64_t *field_lo, uint64_t *field_hi, unsigned long long *n_hard, uint64_t *hard_list,
+                      uint64_t hard_cap, cudaStream_t st)
+{
+  csv_parse_kernel<<<csv_grid(n_lines, 256), 256, 0, st>>>(text, n, line_end, n_newlines, n_lines, column, sep, value, flag8, field_lo, field_hi, n_hard,
+                                                            hard_list, hard_cap);
+  count_launch(1);
+}
+
+void launch_csv_compact(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out, uint64_t out_cap, cudaStream_t st)
+{
+  csv_compact_kernel<<<csv_grid(n_lines, 256), 256, 0, st>>>(value, flag8, pos, n_lines, out, out_cap);
+  count_launch(1);
+}
+
+uint64_t csv_tiles(uint64_t n) { return (n + kCsvTile - 1) / kCsvTile; }
+
+}  // namespace dc

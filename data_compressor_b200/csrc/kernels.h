@@ -146,6 +146,15 @@ void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t
 // ---- aggregate (granularity reduction): out[c][g] = sum of in[c][g*k .. g*k+k), strictly sequential float32 adds
 void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *out, cudaStream_t st);
 
+// ---- csv (decode csv: one text column -> float32), see csv_kernels.cu
+uint64_t csv_tiles(uint64_t n);
+void launch_csv_count(const uint8_t *text, uint64_t n, uint64_t *tile_bits, cudaStream_t st);
+void launch_csv_lines(const uint8_t *text, uint64_t n, const uint64_t *tile_off, uint64_t *line_end, cudaStream_t st);
+void launch_csv_parse(const uint8_t *text, uint64_t n, const uint64_t *line_end, uint64_t n_newlines, uint64_t n_lines, uint32_t column, uint8_t sep,
+                      float *value, uint64_t *flag8, uint64_t *field_lo, uint64_t *field_hi, unsigned long long *n_hard, uint64_t *hard_list,
+                      uint64_t hard_cap, cudaStream_t st);
+void launch_csv_compact(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out, uint64_t out_cap, cudaStream_t st);
+
 // ---- LZMH ------------------------------------------------------------------------------------------------
 struct LzmhArgs
 {

@@ -87,6 +87,16 @@ class Oracle:
         rc, raw, nb = self.run_chain(DEGA_DEC, payload, nbits, vs, nf, adaptive, out_cap=out_cap)
         return rc, np.frombuffer(raw[: (nb // 32) * 4], dtype=np.float32).copy()
 
+    def csv_decode(self, text, column: int = 1, separator: str = ",") -> np.ndarray:
+        """`decode csv` (csv.c:13-44) on a text buffer."""
+        src = np.frombuffer(text.encode() if isinstance(text, str) else bytes(text), dtype=np.uint8)
+        self.lib.dco_csv_decode.restype = C.c_uint64
+        self.lib.dco_csv_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_char, C.c_void_p, C.c_uint64]
+        out = np.empty(src.size + 1, dtype=np.float32)
+        n = int(self.lib.dco_csv_decode(src.ctypes.data if src.size else None, src.size, int(column), separator.encode()[:1],
+                                        out.ctypes.data, out.size))
+        return out[:n].copy()
+
     def aggregate(self, samples, num_values: int) -> np.ndarray:
         """`encode aggregate num_values=k` on one channel (aggregate.c:9-27)."""
         x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
@@ -116,6 +126,20 @@ class Ref:
     @staticmethod
     def available() -> bool:
         return os.path.exists(REF_SO)
+
+    def csv_decode(self, text, column: int = 1, separator: str = ",") -> np.ndarray:
+        """`decode csv` through the reference's own ReadCSV()."""
+        if not hasattr(self.lib, "ref_csv_decode"):
+            raise RuntimeError("oracle/_ref/libdcref.so predates ref_csv_decode: rebuild it where /root/reference exists")
+        self.lib.ref_csv_decode.restype = C.c_longlong
+        self.lib.ref_csv_decode.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_char, C.c_void_p, C.c_ulonglong]
+        src = np.frombuffer(text.encode() if isinstance(text, str) else bytes(text), dtype=np.uint8)
+        out = np.empty(src.size + 1, dtype=np.float32)
+        n = int(self.lib.ref_csv_decode(src.ctypes.data if src.size else None, src.size, int(column), separator.encode()[:1],
+                                        out.ctypes.data, out.size))
+        if n < 0:
+            raise RuntimeError(f"reference csv failed: {n}")
+        return out[:n].copy()
 
     def aggregate(self, samples, num_values: int) -> np.ndarray:
         """`encode aggregate num_values=k` through the reference's own Aggregate()."""

@@ -940,6 +940,42 @@ int dco_dega_decode(const uint8_t *in, uint64_t in_bits, unsigned vs, float nf, 
   return ret;
 }
 
+/* csv.c:13-44.  One character per pass (csv.c:22); a field ends at the separator, at a newline or with the input
+   (csv.c:23); the last character of the input joins the wanted column's text whatever it is (csv.c:25-26); the
+   wanted column goes through strtof (csv.c:27-35); a newline resets the column counter (csv.c:41-42).  The
+   reference's text buffer holds 48 characters; longer fields are undefined there and cut here. */
+uint64_t dco_csv_decode(const uint8_t *text, uint64_t nbytes, unsigned column, char separator, float *out, uint64_t cap)
+{
+  char buffer[64];
+  size_t used = 0;
+  unsigned col = 1;
+  uint64_t i, n = 0;
+  for (i = 0; i < nbytes; i++)
+  {
+    const char ch = (char)text[i];
+    const int at_end = i + 1 == nbytes;
+    if (ch == separator || ch == '\n' || at_end)
+    {
+      if (at_end && col == column && used < sizeof(buffer) - 1)
+        buffer[used++] = ch;
+      if (col == column)
+      {
+        buffer[used] = '\0';
+        if (n < cap)
+          out[n] = strtof(buffer, NULL);
+        n++;
+        used = 0;
+      }
+      col++;
+    }
+    else if (col == column && used < sizeof(buffer) - 1)
+      buffer[used++] = ch;
+    if (ch == '\n')
+      col = 1;
+  }
+  return n;
+}
+
 /* aggregate.c:9-27.  The outer loop runs while input remains (aggregate.c:11); each pass starts a sum at 0
    (aggregate.c:13), adds up to num_values values in order (aggregate.c:16-20) and stops early when the input
    ends (aggregate.c:21-22).  volatile keeps the adds separately rounded and in order whatever the flags. */

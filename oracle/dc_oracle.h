@@ -80,6 +80,10 @@ int dco_dega_decode(const uint8_t *in, uint64_t in_bits, unsigned vs, float nf, 
 
 /* Batch helper for the CPU baseline: encodes `nstreams` uniform streams of `len` samples one after
    another (single thread, like one DCCLI process per stream) and returns the total payload bytes. */
+/* csv.c:13-44 (`decode csv column=.. separator=..`, ReadCSV) on nbytes of text: writes the column's values to out
+   (capacity cap) and returns how many there are. */
+uint64_t dco_csv_decode(const uint8_t *text, uint64_t nbytes, unsigned column, char separator, float *out, uint64_t cap);
+
 /* aggregate.c:9-27 (`encode aggregate num_values=k`) on n float32 values: writes ceil(n / k) sums to out (sequential
    float32 adds from 0.0f, last group may be short) and returns that count. */
 uint64_t dco_aggregate(const float *in, uint64_t n, unsigned num_values, float *out);

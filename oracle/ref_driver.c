@@ -201,3 +201,51 @@ long long ref_aggregate(const float *in, unsigned long long n, unsigned num_valu
   mem_bits_close(&b);
   return ret != NO_ERROR ? (long long)ret : (long long)got_total;
 }
+
+/* `decode csv column=.. separator=..` (DCLib/src/csv.c:13-44) on nbytes of text through the real codec.
+   Returns the number of floats written to out (capacity out_cap) or a negative error code. */
+long long ref_csv_decode(const unsigned char *text, unsigned long long nbytes, unsigned column, char separator, float *out,
+                         unsigned long long out_cap)
+{
+  mem_bits a, b;
+  options_t opt;
+  const enc_dec_t *ed = GetEncoder("csv");
+  io_int_t ret;
+  unsigned long long got_total = 0;
+  a.fb = b.fb = NULL;
+  a.bb = b.bb = NULL;
+  if (ed == NULL || ed->decoder == NULL)
+    return ERROR_INVALID_VALUE;
+  if (mem_bits_open(&a, FBM_WRITING) != NO_ERROR || mem_bits_open(&b, FBM_WRITING) != NO_ERROR)
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_INIT;
+  }
+  if (nbytes > 0 && WriteBitFileBuffer(a.bb, text, (size_t)(nbytes * 8)) != (io_int_t)(nbytes * 8))
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_CALL;
+  }
+  SetBitFileBufferMode(a.bb, FBM_READING);
+  memset(&opt, 0, sizeof(opt));
+  SetDefaultOptions(&opt);
+  opt.error_log_file = NULL;
+  opt.encode = 0;
+  opt.encoder_decoder = ed;
+  opt.column = column;
+  opt.separator_char = separator;
+  ret = (*ed->decoder)(a.bb, b.bb, &opt);
+  SetBitFileBufferMode(b.bb, FBM_READING);
+  while (ret == NO_ERROR && !EndOfBitFileBuffer(b.bb) && got_total < out_cap)
+  {
+    io_int_t got = ReadBitFileBuffer(b.bb, (unsigned char *)(out + got_total), 32);
+    if (got != 32)
+      break;
+    got_total++;
+  }
+  mem_bits_close(&a);
+  mem_bits_close(&b);
+  return ret != NO_ERROR ? (long long)ret : (long long)got_total;
+}

@@ -430,3 +430,39 @@ def test_denormalize_division_is_ieee_for_any_factor(ctx, oracle, nf):
     for c in range(x.shape[0]):
         rc, want = oracle.dega_decode(enc.stream_bytes(c), int(enc.bit_len[c]), nf=nf, out_cap=x.shape[1] * 4 + 64)
         assert rc == 0 and np.array_equal(got[c].view(np.uint32), want.view(np.uint32)), (nf, c)
+
+
+# ---- csv -------------------------------------------------------------------------------------------
+def _same_floats(a, b):
+    return a.size == b.size and np.array_equal(a.view(np.uint32)[a == a], b.view(np.uint32)[b == b]) and np.array_equal(a != a, b != b)
+
+
+def test_csv_decode_matches_oracle(ctx, oracle, golden):
+    """dc_csv_decode_host against the oracle (pinned to the reference's ReadCSV by tests/test_oracle_vs_ref.py): quirks of
+    the reference's character loop, fields strtof has to convert (exponents, hex, inf/nan, long digit strings), random
+    decimals, and the reference's own test file re-printed with two decimals."""
+    from test_oracle_vs_ref import CSV_CASES
+    rng = np.random.default_rng(17)
+    cases = list(CSV_CASES)
+    for _ in range(20):
+        n, d = int(rng.integers(1, 3000)), int(rng.integers(0, 10))
+        rows = [",".join(f"{rng.integers(-10 ** 7, 10 ** 7) / 10 ** d:.{d}f}" for _ in range(int(rng.integers(1, 4)))) for _ in range(n)]
+        cases.append("\n".join(rows) + ("\n" if rng.random() < 0.7 else ""))
+    for t in cases:
+        for col in (1, 2, 3):
+            for sep in (",", ";"):
+                assert _same_floats(ctx.csv_decode(t, col, sep), oracle.csv_decode(t, col, sep)), (t[:40], col, sep)
+    text = "".join(f"{v:.2f}\n" for v in golden.testfile)              # DCCLI/testdata/input.txt has this form (SURVEY 2, row 17)
+    got = ctx.csv_decode(text)
+    assert np.array_equal(got.view(np.uint32), golden.testfile.view(np.uint32))
+    assert np.array_equal(got.view(np.uint32), oracle.csv_decode(text).view(np.uint32))
+
+
+def test_csv_to_dega_pipeline(ctx, oracle, golden):
+    """`decode csv # encode normalize # encode diff # encode seg # encode bac adaptive` with every stage on the GPU gives the
+    bytes of the reference chain on the same text (169 327 bytes for the test file)."""
+    text = "".join(f"{v:.2f}\n" for v in golden.testfile)
+    x = ctx.csv_decode(text)
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda().view(1, -1), block_len=0)
+    g = golden.get("testfile_stage4")
+    assert int(enc.bit_len[0]) == g["out_bits"] and enc.stream_bytes(0) == g["out"].tobytes() and enc.total_bytes == 169327

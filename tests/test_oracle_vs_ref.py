@@ -92,3 +92,32 @@ def test_aggregate_oracle_vs_reference(oracle, ref):
             x[rng.random(n) < 0.05] *= np.float32(-1e-3)      # mixed signs and magnitudes: the order of the adds matters
             a, b = oracle.aggregate(x, k), ref.aggregate(x, k)
             assert a.size == (n + k - 1) // k and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n, k)
+
+
+CSV_CASES = [
+    "1.00\n2.00\n1.50\n", "1.5", "", "\n", "\n\n", "1,2,3\n4,5\n6,7,8", "1,2,", "1,2,\n", "a,b\n,,\n\n5", "12.5\r\n13\r\n",
+    "-0\n+3.25\n 7\n1e3\n0x10\ninf\nnan\n-.5\n5.\n.\n-\n123456789\n0.000012345\n1234.500000\n16777217\n3.4028236e38\n",
+    "  \t9.75x\n1.2.3\n--4\n+-4\n1e\n1e+\n0x\n0xg\nINFINITY\nNaN(12)\n00012.50\n-000.0100\n99999999999999999999\n0.1234567891\n",
+    "3;4;5\n6;7\n", "7\n8",
+]
+
+
+def _same_floats(a, b):
+    return a.size == b.size and np.array_equal(a.view(np.uint32)[a == a], b.view(np.uint32)[b == b]) and np.array_equal(a != a, b != b)
+
+
+def test_csv_decode_oracle_vs_reference(oracle, ref):
+    """`decode csv` (csv.c:13-44): field splitting, column selection, the end-of-input rules and strtof's grammar."""
+    rng = np.random.default_rng(17)
+    cases = list(CSV_CASES)
+    for _ in range(30):     # random decimals with 0..9 fraction digits, sometimes three columns, sometimes no last newline
+        n, d = int(rng.integers(1, 200)), int(rng.integers(0, 10))
+        rows = []
+        for _ in range(n):
+            vals = [f"{rng.integers(-10 ** 7, 10 ** 7) / 10 ** d:.{d}f}" for _ in range(int(rng.integers(1, 4)))]
+            rows.append(",".join(vals))
+        cases.append("\n".join(rows) + ("\n" if rng.random() < 0.7 else ""))
+    for t in cases:
+        for col in (1, 2, 3):
+            for sep in (",", ";"):
+                assert _same_floats(oracle.csv_decode(t, col, sep), ref.csv_decode(t, col, sep)), (t[:40], col, sep)
