@@ -798,7 +798,7 @@ int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t
   // phase 2 (arena): per-line results
   const uint64_t hard_cap = n_lines < (1ull << 20) ? n_lines : (1ull << 20);
   const uint64_t scan_tmp2 = (n_lines + 4095) / 4096 + 2;
-  rc = arena_reserve(c, 5 * Bump::size_of(n_lines + 1, 8) + Bump::size_of(n_lines, 4) + Bump::size_of(out_cap, 4) + Bump::size_of(hard_cap, 8) +
+  rc = arena_reserve(c, 5 * Bump::size_of(n_lines + 1, 8) + Bump::size_of(n_lines, 4) + Bump::size_of(out_cap, 4) + 4 * Bump::size_of(hard_cap, 8) +
                             Bump::size_of(scan_tmp2, 8) + Bump::size_of(8, 8) + 4096);
   if (rc != DC_OK)
     return rc;
@@ -811,6 +811,7 @@ int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t
   float *d_value = ba.take<float>(n_lines);
   float *d_out = ba.take<float>(out_cap);
   uint64_t *d_hard = ba.take<uint64_t>(hard_cap);
+  uint64_t *d_packed = ba.take<uint64_t>(3 * hard_cap);
   uint64_t *d_tmp2 = ba.take<uint64_t>(scan_tmp2);
   unsigned long long *d_nhard = reinterpret_cast<unsigned long long *>(ba.take<uint64_t>(8));
   CU_TRY(c, cudaMemsetAsync(d_nhard, 0, sizeof(unsigned long long), c->stream), DC_ERR_LIBRARY_CALL);
@@ -844,15 +845,17 @@ int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t
   // fields outside the fast grammar (exponents, hex floats, inf/nan, long digit strings): strtof itself, like csv.c:31
   if (n_hard)
   {
-    std::vector<uint64_t> idx(n_hard), lo(n_hard), hi(n_hard), pos(n_hard);
-    CU_TRY(c, cudaMemcpy(idx.data(), d_hard, n_hard * 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
+    std::vector<uint64_t> packed(3 * n_hard);
+    launch_csv_hard(d_hard, n_hard, d_lo, d_hi, d_pos, d_packed, c->stream);
+    if ((rc = check_launch(c, "csv hard fields")) != DC_OK)
+      return rc;
+    CU_TRY(c, cudaMemcpyAsync(packed.data(), d_packed, 3 * n_hard * 8, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+    std::string field;
     for (uint64_t h = 0; h < n_hard; h++)
     {
-      CU_TRY(c, cudaMemcpy(&lo[h], d_lo + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
-      CU_TRY(c, cudaMemcpy(&hi[h], d_hi + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
-      CU_TRY(c, cudaMemcpy(&pos[h], d_pos + idx[h], 8, cudaMemcpyDeviceToHost), DC_ERR_LIBRARY_CALL);
-      std::string field(reinterpret_cast<const char *>(text) + lo[h], hi[h] - lo[h]);
-      out[pos[h]] = strtof(field.c_str(), nullptr);
+      field.assign(reinterpret_cast<const char *>(text) + packed[h], packed[n_hard + h] - packed[h]);
+      out[packed[2 * n_hard + h]] = strtof(field.c_str(), nullptr);
     }
   }
   return DC_OK;

@@ -225,6 +225,29 @@ void launch_csv_parse(const uint8_t *text, uint64_t n, const uint64_t *line_end,
   count_launch(1);
 }
 
+// lo / hi / output position of the fields the host converts, packed in hard-list order (three bulk copies instead of
+// three per field)
+__global__ void __launch_bounds__(256) csv_hard_kernel(const uint64_t *hard_list, uint64_t n_hard, const uint64_t *field_lo, const uint64_t *field_hi,
+                                                       const uint64_t *pos, uint64_t *packed)
+{
+  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_hard; h += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint64_t j = hard_list[h];
+    packed[h] = field_lo[j];
+    packed[n_hard + h] = field_hi[j];
+    packed[2 * n_hard + h] = pos[j];
+  }
+}
+
+void launch_csv_hard(const uint64_t *hard_list, uint64_t n_hard, const uint64_t *field_lo, const uint64_t *field_hi, const uint64_t *pos,
+                     uint64_t *packed, cudaStream_t st)
+{
+  if (n_hard == 0)
+    return;
+  csv_hard_kernel<<<csv_grid(n_hard, 256), 256, 0, st>>>(hard_list, n_hard, field_lo, field_hi, pos, packed);
+  count_launch(1);
+}
+
 void launch_csv_compact(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out, uint64_t out_cap, cudaStream_t st)
 {
   csv_compact_kernel<<<csv_grid(n_lines, 256), 256, 0, st>>>(value, flag8, pos, n_lines, out, out_cap);

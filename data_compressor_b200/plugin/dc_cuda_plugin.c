@@ -170,3 +170,43 @@ DEFINE_STAGE_PLUGIN(EncodeBAC, EncodeBAC_CUDA, DC_STAGE_BAC_ENC)                
 DEFINE_STAGE_PLUGIN(DecodeBAC, DecodeBAC_CUDA, DC_STAGE_BAC_DEC)                               /* bac.c:244      */
 DEFINE_STAGE_PLUGIN(EncodeLZMH, EncodeLZMH_CUDA, DC_STAGE_LZMH_ENC)                            /* lzmh.c:130     */
 DEFINE_STAGE_PLUGIN(DecodeLZMH, DecodeLZMH_CUDA, DC_STAGE_LZMH_DEC)                            /* lzmh.c:383     */
+
+/* ---- text input ------------------------------------------------------------------------------------------------ */
+/* `decode csv [column=..] [separator_char=..]` (csv.c:13).  csv.c defines ReadCSV and WriteCSV in one file, so this one
+   always carries its own name; a build that wants it behind the unchanged "csv" registry row compiles enc_dec.c with
+   -DReadCSV=ReadCSV_CUDA (oracle/Makefile does that for oracle/_ref/DCCLI_cuda). */
+io_int_t ReadCSV_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options)
+{
+  dc_ctx *ctx;
+  uint8_t *in_data;
+  float *values;
+  io_uint_t in_bits, i;
+  uint64_t capacity = 1, count = 0;
+  io_int_t ret;
+  if ((ret = GetContext(&ctx, options->error_log_file)) != NO_ERROR)
+    return ret;
+  if ((ret = DrainInput(in_bit_buf, &in_data, &in_bits)) != NO_ERROR)
+    return ret;
+  for (i = 0; i < in_bits / 8; i++) /* At most one value per line */
+    capacity += in_data[i] == '\n';
+  if ((values = (float*)malloc((size_t)capacity * sizeof(float))) == NULL)
+  {
+    free(in_data);
+    return ERROR_MEMORY;
+  }
+  ret = dc_csv_decode_host(ctx, in_data, in_bits / 8, (uint32_t)options->column, options->separator_char, values, capacity, &count);
+  free(in_data);
+  if (ret != NO_ERROR)
+  {
+    free(values);
+    if (ret == ERROR_LIBRARY_CALL || ret == ERROR_LIBRARY_INIT)
+      LOG_ERROR(options->error_log_file, "CUDA csv reader failed: %s\n", dc_last_error(ctx));
+    return ret;
+  }
+  if (count > 0)
+  {
+    WRITE_BITS_CHECKED_WITH_ACTION_ON_ERROR((const uint8_t*)values, (size_t)(32 * count), out_bit_buf, options->error_log_file, free(values));
+  }
+  free(values);
+  return NO_ERROR;
+}

@@ -64,3 +64,18 @@ def test_errors_propagate_like_the_reference(testfile):
     rc_cpu = run(CPU, neg, a, DEGA)
     rc_gpu = run(GPU, neg, b, DEGA)
     assert rc_cpu == rc_gpu != 0          # ERROR_LIBRARY_CALL as exit status (cli.c:447-453)
+
+
+@pytest.mark.parametrize("options", ["", "column=2", "column=2 separator_char=;", "column=3 separator_char=;"])
+def test_csv_reader_behind_the_unchanged_registry_row(testfile, options):
+    """`decode csv ...` of DCCLI_cuda is the plugin's ReadCSV_CUDA (oracle/Makefile binds the "csv" row's reader to it);
+    ragged rows, both separators, exponent / hex / inf fields that take the strtof route, no newline at the end."""
+    d, _ = testfile
+    src = str(d / "table.csv")
+    rows = ["1.5;2.25;3", "4;5.75", "6;7;8", "1,2,3", "-0.25,1e3,0x1p4", ",inf,", "", "12345678.9,0.000001,99", "7,8"]
+    open(src, "w").write("\n".join(rows))
+    a, b = str(d / "c_cpu.bin"), str(d / "c_gpu.bin")
+    chain = ("decode csv " + options).strip()
+    assert run(CPU, src, a, chain) == 0
+    assert run(GPU, src, b, chain) == 0
+    assert open(a, "rb").read() == open(b, "rb").read() and os.path.getsize(a) > 0
