@@ -86,6 +86,7 @@ SYMBOLS = {
     "dc_lzmh_decode_device": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _P, _P, _P]),
     "dc_aggregate_device": (_I, [_P, _P, _U64, _U64, C.c_uint32, _P]),
     "dc_csv_decode_host": (_I, [_P, _P, _U64, C.c_uint32, C.c_char, _P, _U64, _PU64]),
+    "dc_csv_encode_host": (_I, [_P, _P, _U64, C.c_uint32, C.c_char, C.c_uint32, _P, _U64, _PU64]),
     "dc_container_init_header": (_I, [_PH, C.c_uint32, _PP, _PL, _U64, _U64]),
     "dc_container_create": (_I, [C.c_char_p, _PH]),
     "dc_container_write_shard": (_I, [C.c_char_p, _PH, _U64, _U64, _P, _U64, _P, _U64]),

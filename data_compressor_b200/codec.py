@@ -185,6 +185,21 @@ class Context:
         self._check(rc, "dc_csv_decode_host")
         return out[: n.value].copy()
 
+    def csv_encode(self, values, column: int = 1, separator: str = ",", decimals: int = 2) -> bytes:
+        """`encode csv column=.. separator_char=.. num_decimal_places=..` (DCLib/src/csv.c:46-65): the text of the values."""
+        x = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        cap = x.size * (column + 15) + 64               # values below 10^7 fit; larger ones take the retry
+        n = C.c_uint64(0)
+        for _ in range(2):
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self.lib.dc_csv_encode_host(self.h, x.ctypes.data if x.size else None, x.size, int(column), separator.encode()[:1], int(decimals),
+                                             out.ctypes.data, cap, C.byref(n))
+            if rc != _lib.ERR_MEMORY or n.value <= cap:
+                break
+            cap = int(n.value)
+        self._check(rc, "dc_csv_encode_host")
+        return out[: n.value].tobytes()
+
     # ---- aggregate: granularity reduction ---------------------------------------------------------
     def aggregate(self, x: torch.Tensor, num_values: int) -> torch.Tensor:
         """`encode aggregate num_values=k` (DCLib/src/aggregate.c:9-27) for every channel of a float32

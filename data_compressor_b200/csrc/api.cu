@@ -861,6 +861,51 @@ int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t
   return DC_OK;
 }
 
+int dc_csv_encode_host(dc_ctx *c, const float *values, uint64_t n, uint32_t column, char separator, uint32_t num_decimal_places, uint8_t *text,
+                       uint64_t text_cap, uint64_t *n_out)
+{
+  if (!c || column == 0 || num_decimal_places > 6 || (n && !values) || !n_out)
+    return DC_ERR_INVALID_VALUE;
+  *n_out = 0;
+  if (n == 0)
+    return DC_OK;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  c->ev_mask = 0;
+  const uint64_t scan_tmp = (n + 4095) / 4096 + 2;
+  int rc = stage_reserve(c, Bump::size_of(n, 4) + 4096);
+  if (rc != DC_OK)
+    return rc;
+  if ((rc = arena_reserve(c, 2 * Bump::size_of(n + 1, 8) + Bump::size_of(scan_tmp, 8) + Bump::size_of(text_cap + 64, 1) + 4096)) != DC_OK)
+    return rc;
+  Bump bs(c->stage), ba(c->arena);
+  float *d_values = bs.take<float>(n);
+  uint64_t *d_len = ba.take<uint64_t>(n + 1);
+  uint64_t *d_pos = ba.take<uint64_t>(n + 1);
+  uint64_t *d_tmp = ba.take<uint64_t>(scan_tmp);
+  uint8_t *d_text = ba.take<uint8_t>(text_cap + 64);
+  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaMemcpyAsync(d_values, values, n * sizeof(float), cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+  launch_csv_measure(d_values, n, num_decimal_places, column - 1, d_len, c->stream);
+  launch_byte_scan(d_len, n, d_pos, d_tmp, c->stream);
+  if ((rc = check_launch(c, "csv measure")) != DC_OK)
+    return rc;
+  uint64_t total = 0;
+  if ((rc = read_back(c, d_pos + n, &total, 1)) != DC_OK)
+    return rc;
+  *n_out = total;
+  if (total > text_cap)
+  {
+    set_err(c, "csv text needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)text_cap);
+    return DC_ERR_MEMORY;
+  }
+  launch_csv_write(d_values, n, num_decimal_places, column - 1, (uint8_t)separator, d_pos, d_text, c->stream);
+  if ((rc = check_launch(c, "csv write")) != DC_OK)
+    return rc;
+  CU_TRY(c, cudaMemcpyAsync(text, d_text, total, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+  return DC_OK;
+}
+
 // ---- DEGA, host buffers ----------------------------------------------------------------------------------
 // Channel chunks of the host-buffer calls: the copy of chunk k+1 (and the copy-back of chunk k-1) overlaps the kernels
 // of chunk k.  These calls are bound by the PCIe copies (1.4 GB in, 0.5 GB out for config 2 against ~15 ms of kernels),

@@ -1,4 +1,7 @@
-// csv_kernels.cu -- `decode csv` (DCLib/src/csv.c:13-44, ReadCSV) on the device: one column of a text file -> float32.
+// csv_kernels.cu -- the csv codec on the device.  `decode csv` (DCLib/src/csv.c:13-44, ReadCSV): one column of a text
+// file -> float32, described next; `encode csv` (csv.c:46-65, WriteCSV): float32 -> text, at the end of the file and in
+// csv_device.cuh.
+//
 //
 // ReadCSV walks the text character by character: fields end at the separator, at '\n' or at the end of the input,
 // '\n' resets the column counter, and every time the wanted column ends its text goes through strtof (csv.c:22-35).
@@ -16,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "csv_device.cuh"
 #include "kernels.h"
 
 namespace dc {
@@ -251,6 +255,42 @@ void launch_csv_hard(const uint64_t *hard_list, uint64_t n_hard, const uint64_t 
 void launch_csv_compact(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out, uint64_t out_cap, cudaStream_t st)
 {
   csv_compact_kernel<<<csv_grid(n_lines, 256), 256, 0, st>>>(value, flag8, pos, n_lines, out, out_cap);
+  count_launch(1);
+}
+
+// ---- `encode csv` (csv.c:46-65): float32 -> text ----------------------------------------------------------------
+// One thread per value, two passes around a scan: the length of every line (prefix separators of the empty columns
+// before the wanted one, csv.c:55-58, plus the printed value), then the text itself at the scanned byte position.
+// Neighbouring threads write neighbouring byte ranges, so the byte stores of a warp merge into a few sectors in L2.
+__global__ void __launch_bounds__(256) csv_measure_kernel(const uint32_t *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint64_t *len_bits)
+{
+  // in bits: the scan shared with the coder (launch_byte_scan) turns bit counts into byte offsets
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
+    len_bits[j] = 8 * ((uint64_t)prefix + csv_print<false>(values[j], decimals, nullptr));
+}
+
+__global__ void __launch_bounds__(256) csv_write_kernel(const uint32_t *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint8_t sep,
+                                                        const uint64_t *pos, uint8_t *text)
+{
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
+  {
+    uint8_t *dst = text + pos[j];
+    for (uint32_t k = 0; k < prefix; k++)
+      dst[k] = sep;
+    csv_print<true>(values[j], decimals, dst + prefix);
+  }
+}
+
+void launch_csv_measure(const float *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint64_t *len, cudaStream_t st)
+{
+  csv_measure_kernel<<<csv_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(values), n, decimals, prefix, len);
+  count_launch(1);
+}
+
+void launch_csv_write(const float *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint8_t sep, const uint64_t *pos, uint8_t *text,
+                      cudaStream_t st)
+{
+  csv_write_kernel<<<csv_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(values), n, decimals, prefix, sep, pos, text);
   count_launch(1);
 }
 

@@ -153,6 +153,9 @@ void launch_csv_lines(const uint8_t *text, uint64_t n, const uint64_t *tile_off,
 void launch_csv_parse(const uint8_t *text, uint64_t n, const uint64_t *line_end, uint64_t n_newlines, uint64_t n_lines, uint32_t column, uint8_t sep,
                       float *value, uint64_t *flag8, uint64_t *field_lo, uint64_t *field_hi, unsigned long long *n_hard, uint64_t *hard_list,
                       uint64_t hard_cap, cudaStream_t st);
+void launch_csv_measure(const float *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint64_t *len, cudaStream_t st);
+void launch_csv_write(const float *values, uint64_t n, uint32_t decimals, uint32_t prefix, uint8_t sep, const uint64_t *pos, uint8_t *text,
+                      cudaStream_t st);
 void launch_csv_hard(const uint64_t *hard_list, uint64_t n_hard, const uint64_t *field_lo, const uint64_t *field_hi, const uint64_t *pos,
                      uint64_t *packed, cudaStream_t st);
 void launch_csv_compact(const float *value, const uint64_t *flag8, const uint64_t *pos, uint64_t n_lines, float *out, uint64_t out_cap, cudaStream_t st);

@@ -210,3 +210,57 @@ io_int_t ReadCSV_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * 
   free(values);
   return NO_ERROR;
 }
+
+/* `encode csv [column=..] [separator_char=..] [num_decimal_places=..]` (csv.c:46); same naming rule as ReadCSV_CUDA. */
+io_int_t WriteCSV_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options)
+{
+  dc_ctx *ctx;
+  uint8_t *in_data, *text;
+  io_uint_t in_bits;
+  uint64_t capacity, count = 0, n;
+  io_int_t ret;
+  int attempt;
+  if ((ret = GetContext(&ctx, options->error_log_file)) != NO_ERROR)
+    return ret;
+  if ((ret = DrainInput(in_bit_buf, &in_data, &in_bits)) != NO_ERROR)
+    return ret;
+  n = in_bits / 32;
+  if (in_bits % 32 != 0) /* The reference fails on a partial value: READ_BITS_CHECKED in csv.c:54 */
+  {
+    free(in_data);
+    LOG_ERROR(options->error_log_file, "Could not read %lu bits from input\n", (unsigned long)32);
+    return ERROR_LIBRARY_CALL;
+  }
+  capacity = n * (options->column + 15) + 64; /* Values below 10^7; the library reports the size when it needs more */
+  text = NULL;
+  for (attempt = 0; attempt < 2; attempt++)
+  {
+    if ((text = (uint8_t*)malloc((size_t)capacity)) == NULL)
+    {
+      free(in_data);
+      return ERROR_MEMORY;
+    }
+    ret = dc_csv_encode_host(ctx, (const float*)in_data, n, (uint32_t)options->column, options->separator_char, (uint32_t)options->num_decimal_places,
+                             text, capacity, &count);
+    if (ret != DC_ERR_MEMORY || count <= capacity)
+      break;
+    free(text);
+    text = NULL;
+    capacity = count;
+  }
+  free(in_data);
+  if (ret != NO_ERROR)
+  {
+    if (text != NULL)
+      free(text);
+    if (ret == ERROR_LIBRARY_CALL || ret == ERROR_LIBRARY_INIT)
+      LOG_ERROR(options->error_log_file, "CUDA csv writer failed: %s\n", dc_last_error(ctx));
+    return ret;
+  }
+  if (count > 0)
+  {
+    WRITE_BITS_CHECKED_WITH_ACTION_ON_ERROR(text, (size_t)(8 * count), out_bit_buf, options->error_log_file, free(text));
+  }
+  free(text);
+  return NO_ERROR;
+}

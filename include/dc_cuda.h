@@ -182,6 +182,13 @@ int dc_aggregate_device(dc_ctx *ctx, const float *d_samples, uint64_t n_channels
 int dc_csv_decode_host(dc_ctx *ctx, const uint8_t *text, uint64_t nbytes, uint32_t column, char separator,
                        float *out, uint64_t out_cap, uint64_t *n_out);
 
+/* `encode csv column=c separator_char=s num_decimal_places=d` (DCLib/src/csv.c:46-65, WriteCSV) for n float32 values:
+   per value c - 1 separator characters, then printf's "%.*f" with d <= 6 digits, then '\n'; the text is what the
+   reference's sprintf writes (exact value, round half to even, "-0.00", "inf", "-nan").  *n_out = bytes of text;
+   on DC_ERR_MEMORY it holds the size needed. */
+int dc_csv_encode_host(dc_ctx *ctx, const float *values, uint64_t n, uint32_t column, char separator, uint32_t num_decimal_places,
+                       uint8_t *text, uint64_t text_cap, uint64_t *n_out);
+
 /* ---- container: one file for the streams of a batch encode (host code, no GPU needed) ------- */
 
 /* The reference writes one stream per file (DCIOLib/src/bit_file_buffer.c:310-333 via DCCLI/src/cli.c:129-148).

@@ -97,6 +97,16 @@ class Oracle:
                                         out.ctypes.data, out.size))
         return out[:n].copy()
 
+    def csv_encode(self, values, column: int = 1, separator: str = ",", decimals: int = 2) -> bytes:
+        """`encode csv` (csv.c:46-65): the text of the values."""
+        x = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        self.lib.dco_csv_encode.restype = C.c_uint64
+        self.lib.dco_csv_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_char, C.c_uint, C.c_void_p, C.c_uint64]
+        out = np.empty(x.size * (column + 56) + 16, dtype=np.uint8)
+        n = int(self.lib.dco_csv_encode(x.ctypes.data if x.size else None, x.size, int(column), separator.encode()[:1], int(decimals),
+                                        out.ctypes.data, out.size))
+        return out[:n].tobytes()
+
     def aggregate(self, samples, num_values: int) -> np.ndarray:
         """`encode aggregate num_values=k` on one channel (aggregate.c:9-27)."""
         x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
@@ -140,6 +150,20 @@ class Ref:
         if n < 0:
             raise RuntimeError(f"reference csv failed: {n}")
         return out[:n].copy()
+
+    def csv_encode(self, values, column: int = 1, separator: str = ",", decimals: int = 2) -> bytes:
+        """`encode csv` through the reference's own WriteCSV()."""
+        if not hasattr(self.lib, "ref_csv_encode"):
+            raise RuntimeError("oracle/_ref/libdcref.so predates ref_csv_encode: rebuild it where /root/reference exists")
+        self.lib.ref_csv_encode.restype = C.c_longlong
+        self.lib.ref_csv_encode.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_char, C.c_uint, C.c_void_p, C.c_ulonglong]
+        x = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        out = np.empty(x.size * (column + 56) + 16, dtype=np.uint8)
+        n = int(self.lib.ref_csv_encode(x.ctypes.data if x.size else None, x.size, int(column), separator.encode()[:1], int(decimals),
+                                        out.ctypes.data, out.size))
+        if n < 0:
+            raise RuntimeError(f"reference csv failed: {n}")
+        return out[:n].tobytes()
 
     def aggregate(self, samples, num_values: int) -> np.ndarray:
         """`encode aggregate num_values=k` through the reference's own Aggregate()."""

@@ -9,6 +9,7 @@
  */
 #include "dc_oracle.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -974,6 +975,30 @@ uint64_t dco_csv_decode(const uint8_t *text, uint64_t nbytes, unsigned column, c
       col = 1;
   }
   return n;
+}
+
+/* `encode csv column=.. separator_char=.. num_decimal_places=..` (DCLib/src/csv.c:46-65, WriteCSV): per value,
+   column - 1 separator characters (csv.c:55-58), then printf's "%.*f" of the value with num_decimal_places digits and
+   a newline (csv.c:59-61).  printf is the algorithm here as it is there: the exact binary value, rounded to the
+   requested digits half-to-even, "-" for a set sign bit (also of zero and nan), "inf" / "nan" for the non-finite.
+   Returns the number of bytes the text has; writes at most cap of them. */
+uint64_t dco_csv_encode(const float *in, uint64_t n, unsigned column, char separator, unsigned decimals, uint8_t *out, uint64_t cap)
+{
+  uint64_t i, used = 0;
+  for (i = 0; i < n; i++)
+  {
+    char buffer[64];
+    unsigned k;
+    int len, j;
+    for (k = 1; k < column; k++, used++)
+      if (used < cap)
+        out[used] = (uint8_t)separator;
+    len = snprintf(buffer, sizeof(buffer), "%.*f\n", (int)decimals, (double)in[i]);
+    for (j = 0; j < len; j++, used++)
+      if (used < cap)
+        out[used] = (uint8_t)buffer[j];
+  }
+  return used;
 }
 
 /* aggregate.c:9-27.  The outer loop runs while input remains (aggregate.c:11); each pass starts a sum at 0

@@ -83,6 +83,7 @@ int dco_dega_decode(const uint8_t *in, uint64_t in_bits, unsigned vs, float nf, 
 /* csv.c:13-44 (`decode csv column=.. separator=..`, ReadCSV) on nbytes of text: writes the column's values to out
    (capacity cap) and returns how many there are. */
 uint64_t dco_csv_decode(const uint8_t *text, uint64_t nbytes, unsigned column, char separator, float *out, uint64_t cap);
+uint64_t dco_csv_encode(const float *in, uint64_t n, unsigned column, char separator, unsigned decimals, uint8_t *out, uint64_t cap);
 
 /* aggregate.c:9-27 (`encode aggregate num_values=k`) on n float32 values: writes ceil(n / k) sums to out (sequential
    float32 adds from 0.0f, last group may be short) and returns that count. */

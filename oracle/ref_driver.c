@@ -202,6 +202,55 @@ long long ref_aggregate(const float *in, unsigned long long n, unsigned num_valu
   return ret != NO_ERROR ? (long long)ret : (long long)got_total;
 }
 
+/* `encode csv column=.. separator_char=.. num_decimal_places=..` (DCLib/src/csv.c:46-65) on n floats through the real
+   codec.  Returns the number of text bytes written to out (capacity out_cap) or a negative error code. */
+long long ref_csv_encode(const float *values, unsigned long long n, unsigned column, char separator, unsigned decimals,
+                         unsigned char *out, unsigned long long out_cap)
+{
+  mem_bits a, b;
+  options_t opt;
+  const enc_dec_t *ed = GetEncoder("csv");
+  io_int_t ret;
+  unsigned long long got_total = 0;
+  a.fb = b.fb = NULL;
+  a.bb = b.bb = NULL;
+  if (ed == NULL || ed->encoder == NULL)
+    return ERROR_INVALID_VALUE;
+  if (mem_bits_open(&a, FBM_WRITING) != NO_ERROR || mem_bits_open(&b, FBM_WRITING) != NO_ERROR)
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_INIT;
+  }
+  if (n > 0 && WriteBitFileBuffer(a.bb, (const unsigned char *)values, (size_t)(n * 32)) != (io_int_t)(n * 32))
+  {
+    mem_bits_close(&a);
+    mem_bits_close(&b);
+    return ERROR_LIBRARY_CALL;
+  }
+  SetBitFileBufferMode(a.bb, FBM_READING);
+  memset(&opt, 0, sizeof(opt));
+  SetDefaultOptions(&opt);
+  opt.error_log_file = NULL;
+  opt.encode = 1;
+  opt.encoder_decoder = ed;
+  opt.column = column;
+  opt.separator_char = separator;
+  opt.num_decimal_places = decimals;
+  ret = (*ed->encoder)(a.bb, b.bb, &opt);
+  SetBitFileBufferMode(b.bb, FBM_READING);
+  while (ret == NO_ERROR && !EndOfBitFileBuffer(b.bb) && got_total < out_cap)
+  {
+    io_int_t got = ReadBitFileBuffer(b.bb, out + got_total, 8);
+    if (got != 8)
+      break;
+    got_total++;
+  }
+  mem_bits_close(&a);
+  mem_bits_close(&b);
+  return ret != NO_ERROR ? (long long)ret : (long long)got_total;
+}
+
 /* `decode csv column=.. separator=..` (DCLib/src/csv.c:13-44) on nbytes of text through the real codec.
    Returns the number of floats written to out (capacity out_cap) or a negative error code. */
 long long ref_csv_decode(const unsigned char *text, unsigned long long nbytes, unsigned column, char separator, float *out,

@@ -1,6 +1,6 @@
-"""Throughput of `decode csv` through the C-ABI host call against the reference's ReadCSV (oracle/_ref, one core --
+"""Throughput of `decode csv` and `encode csv` through the C-ABI host call against the reference's ReadCSV (oracle/_ref, one core --
 the reference's csv decoder is a single loop).  Text: the reference's test file printed as "%.2f\\n", repeated.
-Usage: python profiles/csv_decode.py [repeats]        (run on the GPU box; prints one JSON line)"""
+Usage: python profiles/csv_codec.py [repeats]        (run on the GPU box; prints one JSON line)"""
 import ctypes as C
 import json
 import os
@@ -41,6 +41,24 @@ t0 = time.perf_counter()
 r = ref.csv_decode(sample.decode(), 1, ",")
 dt_ref = time.perf_counter() - t0
 assert np.array_equal(r.view(np.uint32), out.numpy()[: r.size].view(np.uint32))
+# `encode csv` of the same values back to text
+txt = torch.empty(text.size + 64, dtype=torch.uint8).pin_memory()
+m = C.c_uint64(0)
+best_e = 1e9
+for it in range(4):
+    t0 = time.perf_counter()
+    rc = ctx.lib.dc_csv_encode_host(ctx.h, out.data_ptr(), n_lines, 1, b",", 2, txt.data_ptr(), txt.numel(), C.byref(m))
+    dt = time.perf_counter() - t0
+    assert rc == 0 and m.value == text.size, (rc, m.value)
+    if it:
+        best_e = min(best_e, dt)
+assert np.array_equal(txt.numpy()[: text.size], text)
+t0 = time.perf_counter()
+rt = ref.csv_encode(r, 1, ",", 2)
+dt_ref_e = time.perf_counter() - t0
+assert rt == sample
+print(json.dumps({"encode_gpu_call_ms": best_e * 1e3, "encode_gpu_text_GBps": text.size / best_e / 1e9, "encode_gpu_Mvalues_per_s": n_lines / best_e / 1e6,
+                  "encode_ref_Mvalues_per_s": r.size / dt_ref_e / 1e6}))
 print(json.dumps({"text_MB": text.size / 1e6, "lines": n_lines, "gpu_call_ms": best * 1e3, "gpu_text_GBps": text.size / best / 1e9,
                   "gpu_Mlines_per_s": n_lines / best / 1e6, "ref_sample_MB": len(sample) / 1e6, "ref_text_GBps": len(sample) / dt_ref / 1e9,
                   "ref_Mlines_per_s": r.size / dt_ref / 1e6}))

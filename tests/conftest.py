@@ -67,7 +67,7 @@ class Sim:
         os.makedirs(os.path.dirname(so), exist_ok=True)
         srcs = [os.path.join(d, "sim.cpp"), os.path.join(d, "host_shim.h")] + \
             [os.path.join(ROOT, "data_compressor_b200", "csrc", f) for f in ("bitio.cuh", "bac.cuh", "dega_device.cuh", "kernels.h",
-                                                                             "lzmh_device.cuh")]
+                                                                             "lzmh_device.cuh", "csv_device.cuh")]
         srcs = [s for s in srcs if os.path.exists(s)]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
@@ -89,7 +89,16 @@ class Sim:
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sim_lzmh_decode.restype = C.c_int
         L.sim_lzmh_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.sim_csv_encode.restype = C.c_uint64
+        L.sim_csv_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_uint64]
         self.lib = L
+
+    def csv_encode(self, values, column=1, separator=",", decimals=2) -> bytes:
+        x = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        out = np.empty(x.size * (column + 56) + 16, dtype=np.uint8)
+        n = int(self.lib.sim_csv_encode(x.ctypes.data if x.size else None, x.size, column, separator.encode()[:1], decimals, out.ctypes.data, out.size))
+        assert n <= out.size
+        return out[:n].tobytes()
 
     def stage_run(self, stage, data, nbits=None, vs=32, nf=100.0, adaptive=0, cap=None):
         src = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) \

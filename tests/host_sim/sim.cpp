@@ -8,6 +8,7 @@
 
 #include "../../data_compressor_b200/csrc/dega_device.cuh"
 #include "../../data_compressor_b200/csrc/lzmh_device.cuh"
+#include "../../data_compressor_b200/csrc/csv_device.cuh"
 #include "../../include/dc_cuda.h"
 
 using namespace dc;
@@ -27,6 +28,25 @@ static const DivEntry *div_table()
 static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
+
+// the two passes of `encode csv` (csv_measure_kernel / csv_write_kernel) over n values, sequentially; returns the text length
+uint64_t sim_csv_encode(const uint32_t *values, uint64_t n, uint32_t column, char sep, uint32_t decimals, uint8_t *text, uint64_t cap)
+{
+  uint64_t pos = 0;
+  for (uint64_t j = 0; j < n; j++)
+  {
+    const uint64_t len = (uint64_t)(column - 1) + dc::csv_print<false>(values[j], decimals, nullptr);
+    if (pos + len <= cap)
+    {
+      for (uint32_t k = 0; k + 1 < column; k++)
+        text[pos + k] = (uint8_t)sep;
+      if (dc::csv_print<true>(values[j], decimals, text + pos + column - 1) + (column - 1) != len)
+        return ~0ull;
+    }
+    pos += len;
+  }
+  return pos;
+}
 
 // how often the arithmetic coder's unrolled groups ran out of room and were redone (which = 0 encoder, 1 decoder)
 uint64_t sim_bac_redo_count(int which) { return g_bac_redo[which & 1]; }

@@ -466,3 +466,20 @@ def test_csv_to_dega_pipeline(ctx, oracle, golden):
     enc = ctx.dega_encode(torch.from_numpy(x).cuda().view(1, -1), block_len=0)
     g = golden.get("testfile_stage4")
     assert int(enc.bit_len[0]) == g["out_bits"] and enc.stream_bytes(0) == g["out"].tobytes() and enc.total_bytes == 169327
+
+
+def test_csv_encode_matches_oracle(ctx, oracle, golden):
+    """dc_csv_encode_host against the oracle (pinned to the reference's WriteCSV in tests/test_oracle_vs_ref.py)."""
+    from test_oracle_vs_ref import csv_encode_values
+    x = csv_encode_values()
+    big = np.array([3.4028235e38, -3.4028235e38, 1e38, 2.0 ** 127, 2.0 ** 100, 2.0 ** 64, 2.0 ** 63], dtype=np.float32)
+    x = np.concatenate([x, big])                        # forces the capacity retry as well
+    for d in range(7):
+        for col, sep in ((1, ","), (4, ";")):
+            assert ctx.csv_encode(x, col, sep, d) == oracle.csv_encode(x, col, sep, d), (d, col)
+    assert ctx.csv_encode(np.zeros(0, np.float32)) == b""
+    text = "".join(f"{v:.2f}\n" for v in golden.testfile).encode()
+    assert ctx.csv_encode(golden.testfile) == text
+    assert ctx.csv_encode(ctx.csv_decode(text)) == text                 # the ends of `make test`
+    big_n = np.tile(golden.testfile, 40)                                # 4 M values: many CTAs, positions beyond 2^24
+    assert ctx.csv_encode(big_n, 2, ",", 3) == oracle.csv_encode(big_n, 2, ",", 3)

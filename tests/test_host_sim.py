@@ -191,3 +191,14 @@ def test_bac_carry_through_stored_words(sim, oracle, adaptive):
                 ff += b"\xff" * 6 in want[1]     # a run resolved downwards: 0111...
                 zz += b"\x00" * 6 in want[1]     # a run resolved by a carry: 1000...
     assert adaptive == 0 or (ff > 20 and zz > 20)   # the static model cannot straddle for long (EOF owns the lowest third)
+
+
+def test_csv_print_matches_oracle(sim, oracle):
+    """The per-value body of `encode csv` (csv_device.cuh) against the oracle's printf, all decimal counts."""
+    from test_oracle_vs_ref import csv_encode_values
+    x = csv_encode_values()
+    big = np.array([3.4028235e38, -3.4028235e38, 1e38, 2.0 ** 127, 2.0 ** 100, 2.0 ** 64, 2.0 ** 63, 1.8446743e19], dtype=np.float32)
+    x = np.concatenate([x, big])                        # the oracle's buffer, unlike the reference's, holds these
+    for d in range(7):
+        for col, sep in ((1, ","), (4, ";")):
+            assert sim.csv_encode(x, col, sep, d) == oracle.csv_encode(x, col, sep, d), (d, col)

@@ -121,3 +121,34 @@ def test_csv_decode_oracle_vs_reference(oracle, ref):
         for col in (1, 2, 3):
             for sep in (",", ";"):
                 assert _same_floats(oracle.csv_decode(t, col, sep), ref.csv_decode(t, col, sep)), (t[:40], col, sep)
+
+
+def csv_encode_values():
+    """Values for `encode csv`: ties of the decimal rounding, signed zeros, denormals, non-finite values, integers beyond
+    2^64, meter-like readings and random bit patterns.  |x| < 1e30: the reference's text buffer (csv.c:11) holds 48
+    characters, which larger values with six decimals overflow."""
+    rng = np.random.default_rng(23)
+    special = np.array([0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 0.375, -0.005, 0.005, 1e-7, 3.4e29, -3.4e29, 1e-45, -1e-45, np.inf, -np.inf, np.nan,
+                        16777216.0, 1e10, 1.8446744e19, 3.6893488e19, 123456.789, 0.045, 0.055, 2.0 ** -24, 1 - 2.0 ** -24, 9.995, 99.995,
+                        0.9999999, 0.95, 0.25, 0.75, 8388608.5, 4194304.25], dtype=np.float32)
+    neg_nan = np.array([0xFFC00000, 0x7F800001, 0xFF800001], dtype=np.uint32).view(np.float32)
+    rnd = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    rnd = rnd[~(np.abs(rnd) >= 1e30)]
+    meter = (rng.integers(0, 10 ** 7, 20000) / 100).astype(np.float32)
+    halves = (rng.integers(0, 2 ** 20, 5000) / 2.0 ** rng.integers(1, 12, 5000)).astype(np.float32)      # exact binary fractions: real ties
+    return np.concatenate([special, neg_nan, rnd, meter, halves])
+
+
+def test_csv_encode_oracle_vs_reference(oracle, ref):
+    """`encode csv` (csv.c:46-65): printf's rounding, the column prefix and the separator."""
+    x = csv_encode_values()
+    for d in range(7):
+        for col, sep in ((1, ","), (3, ";")):
+            assert oracle.csv_encode(x, col, sep, d) == ref.csv_encode(x, col, sep, d), (d, col)
+    assert oracle.csv_encode(np.zeros(0, np.float32)) == ref.csv_encode(np.zeros(0, np.float32)) == b""
+
+
+def test_csv_round_trip_of_the_test_file(oracle, ref, golden):
+    """decode csv # encode csv gives the test file's text back (what `make test` diffs at the end)."""
+    text = "".join(f"{v:.2f}\n" for v in golden.testfile)
+    assert ref.csv_encode(ref.csv_decode(text)) == text.encode() == oracle.csv_encode(oracle.csv_decode(text))
