@@ -795,46 +795,50 @@ int dc_csv_decode_host(dc_ctx *c, const uint8_t *text, uint64_t nbytes, uint32_t
   if ((rc = read_back(c, d_tile_off + tiles, &n_newlines, 1)) != DC_OK)
     return rc;
   const uint64_t n_lines = n_newlines + (text[nbytes - 1] != '\n' ? 1 : 0);   // an unterminated last line counts (csv.c:22)
-  // phase 2 (arena): per-line results
-  const uint64_t hard_cap = n_lines < (1ull << 20) ? n_lines : (1ull << 20);
-  const uint64_t scan_tmp2 = (n_lines + 4095) / 4096 + 2;
-  rc = arena_reserve(c, 5 * Bump::size_of(n_lines + 1, 8) + Bump::size_of(n_lines, 4) + Bump::size_of(out_cap, 4) + 4 * Bump::size_of(hard_cap, 8) +
-                            Bump::size_of(scan_tmp2, 8) + Bump::size_of(8, 8) + 4096);
-  if (rc != DC_OK)
-    return rc;
-  Bump ba(c->arena);
-  uint64_t *d_line_end = ba.take<uint64_t>(n_lines + 1);
-  uint64_t *d_flag8 = ba.take<uint64_t>(n_lines + 1);
-  uint64_t *d_pos = ba.take<uint64_t>(n_lines + 1);
-  uint64_t *d_lo = ba.take<uint64_t>(n_lines + 1);
-  uint64_t *d_hi = ba.take<uint64_t>(n_lines + 1);
-  float *d_value = ba.take<float>(n_lines);
-  float *d_out = ba.take<float>(out_cap);
-  uint64_t *d_hard = ba.take<uint64_t>(hard_cap);
-  uint64_t *d_packed = ba.take<uint64_t>(3 * hard_cap);
-  uint64_t *d_tmp2 = ba.take<uint64_t>(scan_tmp2);
-  unsigned long long *d_nhard = reinterpret_cast<unsigned long long *>(ba.take<uint64_t>(8));
-  CU_TRY(c, cudaMemsetAsync(d_nhard, 0, sizeof(unsigned long long), c->stream), DC_ERR_LIBRARY_CALL);
-  launch_csv_lines(d_text, nbytes, d_tile_off, d_line_end, c->stream);
-  launch_csv_parse(d_text, nbytes, d_line_end, n_newlines, n_lines, column, (uint8_t)separator, d_value, d_flag8, d_lo, d_hi, d_nhard, d_hard,
-                   hard_cap, c->stream);
-  launch_byte_scan(d_flag8, n_lines, d_pos, d_tmp2, c->stream);
-  if ((rc = check_launch(c, "csv parse")) != DC_OK)
-    return rc;
+  // phase 2 (arena): per-line results.  The list of fields that need strtof starts small; a text with more of them than
+  // the list holds (the parse kernel counts them all) runs this phase a second time with the exact size.
+  uint64_t hard_cap = n_lines < (1ull << 16) ? n_lines : (1ull << 16);
+  uint64_t *d_flag8, *d_pos, *d_lo, *d_hi, *d_hard, *d_packed;
+  float *d_value, *d_out;
   uint64_t total = 0, n_hard = 0;
-  if ((rc = read_back(c, d_pos + n_lines, &total, 1)) != DC_OK ||
-      (rc = read_back(c, reinterpret_cast<const uint64_t *>(d_nhard), &n_hard, 1)) != DC_OK)
-    return rc;
+  for (;;)
+  {
+    const uint64_t scan_tmp2 = (n_lines + 4095) / 4096 + 2;
+    rc = arena_reserve(c, 5 * Bump::size_of(n_lines + 1, 8) + Bump::size_of(n_lines, 4) + Bump::size_of(out_cap, 4) + 4 * Bump::size_of(hard_cap, 8) +
+                              Bump::size_of(scan_tmp2, 8) + Bump::size_of(8, 8) + 4096);
+    if (rc != DC_OK)
+      return rc;
+    Bump ba(c->arena);
+    uint64_t *d_line_end = ba.take<uint64_t>(n_lines + 1);
+    d_flag8 = ba.take<uint64_t>(n_lines + 1);
+    d_pos = ba.take<uint64_t>(n_lines + 1);
+    d_lo = ba.take<uint64_t>(n_lines + 1);
+    d_hi = ba.take<uint64_t>(n_lines + 1);
+    d_value = ba.take<float>(n_lines);
+    d_out = ba.take<float>(out_cap);
+    d_hard = ba.take<uint64_t>(hard_cap);
+    d_packed = ba.take<uint64_t>(3 * hard_cap);
+    uint64_t *d_tmp2 = ba.take<uint64_t>(scan_tmp2);
+    unsigned long long *d_nhard = reinterpret_cast<unsigned long long *>(ba.take<uint64_t>(8));
+    CU_TRY(c, cudaMemsetAsync(d_nhard, 0, sizeof(unsigned long long), c->stream), DC_ERR_LIBRARY_CALL);
+    launch_csv_lines(d_text, nbytes, d_tile_off, d_line_end, c->stream);
+    launch_csv_parse(d_text, nbytes, d_line_end, n_newlines, n_lines, column, (uint8_t)separator, d_value, d_flag8, d_lo, d_hi, d_nhard, d_hard,
+                     hard_cap, c->stream);
+    launch_byte_scan(d_flag8, n_lines, d_pos, d_tmp2, c->stream);
+    if ((rc = check_launch(c, "csv parse")) != DC_OK)
+      return rc;
+    if ((rc = read_back(c, d_pos + n_lines, &total, 1)) != DC_OK ||
+        (rc = read_back(c, reinterpret_cast<const uint64_t *>(d_nhard), &n_hard, 1)) != DC_OK)
+      return rc;
+    if (n_hard <= hard_cap)
+      break;
+    hard_cap = n_hard;
+  }
   *n_out = total;
   if (total > out_cap)
   {
     set_err(c, "csv column holds %llu values, capacity is %llu", (unsigned long long)total, (unsigned long long)out_cap);
     return DC_ERR_MEMORY;
-  }
-  if (n_hard > hard_cap)
-  {
-    set_err(c, "%llu fields need strtof, more than the %llu this call keeps track of", (unsigned long long)n_hard, (unsigned long long)hard_cap);
-    return DC_ERR_INVALID_FORMAT;
   }
   launch_csv_compact(d_value, d_flag8, d_pos, n_lines, d_out, out_cap, c->stream);
   if ((rc = check_launch(c, "csv compact")) != DC_OK)

@@ -483,3 +483,13 @@ def test_csv_encode_matches_oracle(ctx, oracle, golden):
     assert ctx.csv_encode(ctx.csv_decode(text)) == text                 # the ends of `make test`
     big_n = np.tile(golden.testfile, 40)                                # 4 M values: many CTAs, positions beyond 2^24
     assert ctx.csv_encode(big_n, 2, ",", 3) == oracle.csv_encode(big_n, 2, ",", 3)
+
+
+def test_csv_decode_many_strtof_fields(ctx, oracle):
+    """More fields outside the fast grammar than the first pass keeps track of (65 536): the parse phase reruns with the
+    exact list size and every one of them still gets strtof's value."""
+    rng = np.random.default_rng(5)
+    vals = rng.integers(1, 10 ** 6, 150000)
+    text = "".join(f"{v}e-2\n" if i % 2 else f"{v / 100:.2f}\n" for i, v in enumerate(vals))
+    got, want = ctx.csv_decode(text), oracle.csv_decode(text)
+    assert got.size == vals.size and np.array_equal(got.view(np.uint32), want.view(np.uint32))
