@@ -9,7 +9,8 @@
 //            lane measures the match length of 4 of the 128 offsets, a REDUX picks (longest, then smallest
 //            offset) -- the same winner as the reference's ascending scan that keeps strictly longer matches only
 //            (lzmh.c:196-214).  The rank list is searched/updated with ballots; lane 0 owns the bit writer.
-//   decoder: one THREAD per stream (bit-serial parse; copies read the thread's own output).
+//   decoder: one WARP per stream too: every lane follows the bit-serial parse, the work inside a token (prefix-code
+//            match, rank-list update, match copy, output to global memory) is shared out over the lanes.
 //
 // The reference works on a 403-byte ring (lzmh.c:68); restated on linear positions the ring always holds
 // min(pos,128) bytes of history and min(remaining,275) bytes of look-ahead, with one visible quirk: an input of
@@ -233,181 +234,332 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
     a.bits_out.nbits[s] = w.overflow ? 0 : bits;
   }
 }
-#endif   // !DC_HOST_SIM
-
 // ---------------------------------------------------------------------------------------------------------
-// Decoder, one thread per stream (lzmh.c:383-574)
-__device__ inline void lzmh_decode_body(const LzmhArgs &a, const uint64_t s)
+// Decoder, one warp per stream (lzmh.c:383-574).
+//
+// The parse is bit-serial and every lane follows it in step (the bit window, the recent offsets and the output
+// position are warp-uniform registers); the lanes share the work inside a token: the 19 prefix codes are matched by
+// 19 lanes and a ballot, the rank list (shared memory) is searched and shifted like in the encoder, a match copy
+// moves 32 bytes per trip.  The last 1024 output bytes live in a shared-memory ring -- the reference's 128-byte
+// history is its tail -- and leave for global memory 512 bytes at a time, 16 bytes per lane.  The compressed input is
+// read 128 bytes at a time, one byte-swapped word per lane, and handed round by a shuffle every 32 bits.
+//
+// The reference keeps a window of `have` <= 25 bits that it tops up bit by bit before every token (lzmh.c:409-413) and
+// stops when the input is used up and the window is empty (lzmh.c:571).  Here the window is the top of a 64-bit
+// accumulator of the stream with zeros behind its last bit, and `rem` counts the bits no token has used yet:
+// have = min(25, rem), "input used up" = rem <= 25 when the token started, "window empty" = accumulator zero.
+// About 45 warp instructions per token; the first version (separate window, 64-bit positions, a division per
+// overlapping copy) took 150.
+static const uint32_t kLzOutRing = 1024;    // bytes of output kept in shared memory per warp (power of two)
+static const uint32_t kLzOutFlush = 512;    // bytes per flush
+static const uint32_t kLzModTab = 32 * 32 + 32;   // [back][lane] = lane % back for back < 32, then [back] = 32 % back
+
+// shared memory through 32-bit addresses (the generic-pointer form recomputes the window base in the token loop)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
 {
-  BitReader r;
-  r.init(src_ptr(a.bits_in, s), a.bits_in.nbits[s]);
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+struct LzWarpBits   // warp-uniform MSB-first bit source
+{
+  const uint32_t *pchunk;   // word 0 of the 32-word chunk the lanes hold in w0 (w1: the chunk after it)
+  const uint32_t *plast;    // the word with the stream's last bit
+  uint32_t last_mask;       // its stream bits
+  uint32_t w0, w1, lane;
+  uint32_t wi;              // next word of the chunk to hand out
+  uint32_t a_hi, a_lo;      // the next 64 bits of the stream, left-aligned, zero beyond its end
+  uint32_t valid;           // how many of them are loaded: 33..64 between tokens
+
+  __device__ __forceinline__ uint32_t load(const uint32_t *p) const
+  {
+    if (p > plast)
+      return 0u;
+    const uint32_t w = __byte_perm(__ldg(p), 0, 0x0123);
+    return p == plast ? w & last_mask : w;
+  }
+  __device__ __forceinline__ uint32_t next_word()
+  {
+    const uint32_t w = __shfl_sync(0xFFFFFFFFu, w0, wi);
+    if (++wi == 32)
+    {
+      wi = 0;
+      pchunk += 32;
+      w0 = w1;
+      w1 = load(pchunk + 32 + lane);
+    }
+    return w;
+  }
+  __device__ __forceinline__ void consume(uint32_t used)   // used < 32
+  {
+    a_hi = __funnelshift_l(a_lo, a_hi, used);
+    a_lo <<= used;
+    valid -= used;
+    if (valid <= 32)   // a_lo is empty: the next word goes `valid` bits below the top
+    {
+      const uint32_t w = next_word();
+      a_hi |= __funnelshift_rc(w, 0u, valid);
+      a_lo = __funnelshift_rc(0u, w, valid);
+      valid += 32;
+    }
+  }
+  __device__ __forceinline__ void init(const uint8_t *p, uint64_t nbits, uint32_t lane_)
+  {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(p - mis);
+    const uint64_t end = mis * 8 + nbits;
+    plast = nbits ? base + ((end - 1) >> 5) : base - 1;
+    last_mask = 0xFFFFFFFFu << (31 - ((uint32_t)(end - 1) & 31));
+    lane = lane_;
+    pchunk = base;
+    w0 = load(base + lane);
+    w1 = load(base + 32 + lane);
+    wi = 0;
+    a_hi = next_word();
+    a_lo = next_word();
+    valid = 64;
+    consume(mis * 8);
+  }
+};
+
+__device__ inline void lzmh_decode_warp(const LzmhArgs &a, const uint64_t s, const uint32_t ring, const uint32_t lsym, const uint32_t lcnt,
+                                        const uint32_t modtab)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  LzWarpBits r;
+  const uint64_t nbits = a.bits_in.nbits[s];
+  r.init(src_ptr(a.bits_in, s), nbits, lane);
+  long long rem = (long long)nbits;   // bits no token has used yet
   uint8_t *out = a.out + a.out_off[s];
   const uint64_t cap = a.out_off[s + 1] - a.out_off[s];
-  uint64_t np = 0;   // bytes produced
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  uint64_t flushed = 0;   // bytes already in global memory (a multiple of kLzOutFlush until the end)
+  uint32_t pend = 0;      // bytes produced since; the produced total is flushed + pend
+  uint32_t rpos = 0;      // the produced total mod 2^32: its low bits are the ring slot of the next byte
 
-  uint32_t window = 0;   // code_sym, lzmh.c:393
-  int have = 0;          // code_length, lzmh.c:394
-  int recent[4] = { 0, 0, 0, 0 };
-  uint8_t lsym[kLzList];
-  uint32_t lcnt[kLzList];
-  for (int i = 0; i < kLzList; i++)
+  for (uint32_t i = lane; i < kLzOutRing / 4; i += 32)   // never-written history reads as zero (lzmh.c:396)
+    sts_u32(ring + 4 * i, 0);
+  for (uint32_t i = lane; i < (uint32_t)kLzList; i += 32)
   {
-    lsym[i] = 0;
-    lcnt[i] = 0;
+    sts_u8(lsym + i, 0);
+    sts_u32(lcnt + 4 * i, 0);
   }
-  int err = 0;
+  __syncwarp();
 
-  // a byte leaves the decoder: output + history (the reference's 128-byte ring is the tail of the output)
-#define LZ_EMIT(byte_)              \
-  do                                \
-  {                                 \
-    if (np < cap)                   \
-      out[np] = (uint8_t)(byte_);   \
-    np++;                           \
-  } while (0)
+  // lane i < 19 matches prefix code i (lzmh.c:86-106)
+  const uint32_t my_len = lz_tree_len((int)lane);
+  const uint32_t my_code = lane < (uint32_t)kLzTree ? lz_tree_code((int)lane) : 0xFFFFFFFFu;
+  int recent0 = 0, recent1 = 0, recent2 = 0, recent3 = 0;
 
-  do
-  {
-    // lzmh.c:409-413: bit-by-bit refill while at least 8 bits are free, i.e. up to 25 buffered bits
-    if (have < 25)
+  // the oldest `n` pending bytes go to global memory; a whole aligned 512-byte piece as one 16-byte store per lane
+  auto flush = [&](uint32_t n) {
+    __syncwarp();
+    const uint32_t slot = (rpos - pend) & (kLzOutRing - 1);
+    if (n == kLzOutFlush && out_aligned && flushed + kLzOutFlush <= cap)
     {
-      const uint64_t av = r.avail();
-      const uint32_t want = (uint32_t)(25 - have);
-      const uint32_t t = av < want ? (uint32_t)av : want;
-      if (t)
-      {
-        window |= r.take(t) << (32 - have - t);
-        have += (int)t;
-      }
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + slot + 16 * lane) : "memory");
+      *reinterpret_cast<uint4 *>(out + flushed + 16 * lane) = v;
     }
-    if (window & 0x80000000u)   // static prefix code -> rank (lzmh.c:414-450)
+    else
+      for (uint32_t i = lane; i < n; i += 32)
+        if (flushed + i < cap)
+          out[flushed + i] = (uint8_t)lds_u8(ring + ((slot + i) & (kLzOutRing - 1)));
+    flushed += n;
+    pend -= n;
+  };
+
+  for (;;)
+  {
+    if (pend >= kLzOutFlush)
+      flush(kLzOutFlush);
+    const uint32_t window = r.a_hi;
+    const bool input_used_up = rem <= 25;   // every remaining bit is in the reference's window: its reader is at EOF
+    uint32_t used;
+    if (window & 0x80000000u)   // static prefix code -> rank (lzmh.c:414-450): the first code that matches
     {
-      int i;
-      for (i = 0; i < kLzTree; i++)
-      {
-        const uint32_t L = lz_tree_len(i);
-        if (have >= (int)L && (window >> (32 - L)) == lz_tree_code(i))
-          break;
-      }
-      if (i == kLzTree)   // lzmh.c:447-449: silent stop
+      const bool hit = (window >> (32 - my_len)) == my_code && (!input_used_up || rem >= (long long)my_len);
+      const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
+      if (hits == 0)   // lzmh.c:447-449: silent stop
         break;
-      const uint32_t L = lz_tree_len(i);
-      have -= (int)L;
-      window <<= L;
-      const uint8_t byte = lsym[i];
-      LZ_EMIT(byte);
-      if (lcnt[i] < 65535u)   // lzmh.c:431-442
+      const int i = __ffs((int)hits) - 1;
+      used = __shfl_sync(0xFFFFFFFFu, my_len, i);
+      const uint32_t byte = lds_u8(lsym + i);
+      const uint32_t c = lds_u32(lcnt + 4 * i);
+      if (lane == 0)
+        sts_u8(ring + (rpos & (kLzOutRing - 1)), byte);
+      rpos++;
+      pend++;
+      if (c < 65535u)   // lzmh.c:431-442: count + 1, move left past strictly smaller counts (they all equal c)
       {
-        const uint32_t c = lcnt[i] + 1;
-        while (i > 0 && c > lcnt[i - 1])
+        const uint32_t c1 = c + 1;
+        const uint32_t lt = __ballot_sync(0xFFFFFFFFu, (int)lane < i && lds_u32(lcnt + 4 * lane) < c1);
+        const int dstpos = lt ? __ffs((int)lt) - 1 : i;
+        const bool moves = (int)lane > dstpos && (int)lane <= i;
+        const uint32_t left = moves ? lds_u8(lsym + lane - 1) : 0;
+        __syncwarp();
+        if (moves)
+          sts_u8(lsym + lane, left);
+        if (lane == 0)
         {
-          lsym[i] = lsym[i - 1];
-          i--;
+          sts_u8(lsym + dstpos, byte);
+          sts_u32(lcnt + 4 * dstpos, c1);
         }
-        lcnt[i] = c & 0xFFFFu;
-        lsym[i] = byte;
+        __syncwarp();
       }
     }
     else if ((window & 0x40000000u) == 0)   // 00 + byte (lzmh.c:451-479)
     {
-      const uint8_t byte = (uint8_t)((window >> 22) & 0xFF);
-      have -= 10;
-      window <<= 10;
-      LZ_EMIT(byte);
-      int pos = 0;
-      while (pos < kLzList && lcnt[pos] > 0 && lsym[pos] != byte)
-        pos++;
-      if (pos < kLzList && lcnt[pos] < 65535u)
+      const uint32_t byte = (window >> 22) & 0xFF;
+      used = 10;
+      if (lane == 0)
+        sts_u8(ring + (rpos & (kLzOutRing - 1)), byte);
+      rpos++;
+      pend++;
+      // first entry that is free or holds the byte
+      const uint32_t i0 = lane, i1 = lane + 32;
+      const bool in1 = i1 < (uint32_t)kLzList;
+      const uint32_t cnt0 = lds_u32(lcnt + 4 * i0), cnt1 = in1 ? lds_u32(lcnt + 4 * i1) : 0;
+      const uint32_t sym0 = lds_u8(lsym + i0), sym1 = in1 ? lds_u8(lsym + i1) : 0;
+      const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cnt0 == 0 || sym0 == byte);
+      const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, in1 && (cnt1 == 0 || sym1 == byte));
+      const int pos = b0 ? __ffs((int)b0) - 1 : b1 ? __ffs((int)b1) + 31 : kLzList;
+      if (pos < kLzList)
       {
-        const uint32_t c = lcnt[pos] + 1;
-        while (pos > 0 && c > lcnt[pos - 1])
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, pos < 32 ? cnt0 : cnt1, pos & 31);
+        if (c < 65535u)
         {
-          lsym[pos] = lsym[pos - 1];
-          lcnt[pos] = lcnt[pos - 1];
-          pos--;
+          const uint32_t c1 = c + 1;
+          const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (int)i0 < pos && cnt0 < c1);
+          const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (int)i1 < pos && cnt1 < c1);
+          const int dstpos = m0 ? __ffs((int)m0) - 1 : m1 ? __ffs((int)m1) + 31 : pos;
+          // entries [dstpos, pos) move one place right (their counts all equal c, so only the symbols move)
+          if ((int)i0 >= dstpos && (int)i0 < pos)
+            sts_u8(lsym + i0 + 1, sym0);
+          if ((int)i1 >= dstpos && (int)i1 < pos)
+            sts_u8(lsym + i1 + 1, sym1);
+          __syncwarp();
+          if (lane == 0)
+          {
+            sts_u8(lsym + dstpos, byte);
+            sts_u32(lcnt + 4 * dstpos, c1);
+          }
+          __syncwarp();
         }
-        lcnt[pos] = c;
-        lsym[pos] = byte;
       }
     }
     else   // 01: LZ token (lzmh.c:480-569)
     {
-      int off, len, k;
-      have -= 2;
-      window <<= 2;
-      if ((window & 0x80000000u) == 0)   // explicit 7-bit offset
+      uint32_t w = window << 2;
+      used = 2;
+      int off, k;
+      if ((w & 0x80000000u) == 0)   // 0 + explicit 7-bit offset
       {
-        off = (int)((window >> 24) & 0x7F) + 1;
-        have -= 8;
-        window <<= 8;
+        off = (int)((w >> 24) & 0x7F) + 1;
+        w <<= 8;
+        used += 8;
         k = 3;
       }
+      else   // recent offsets: 10 -> slot 0, 110 -> 1, 1110 -> 2, 1111 -> 3
+      {
+        const uint32_t ones = (uint32_t)__clz((int)~w);
+        k = ones > 3 ? 3 : (int)ones - 1;
+        const uint32_t n = ones > 3 ? 4u : ones + 1;
+        w <<= n;
+        used += n;
+        off = k == 0 ? recent0 : k == 1 ? recent1 : k == 2 ? recent2 : recent3;
+      }
+      if (k >= 3)
+        recent3 = recent2;
+      if (k >= 2)
+        recent2 = recent1;
+      if (k >= 1)
+        recent1 = recent0;
+      recent0 = off;
+      uint32_t len;
+      if ((w & 0x80000000u) == 0)
+      {
+        len = ((w >> 28) & 0x7) + 3;
+        used += 4;
+      }
+      else if ((w & 0x40000000u) == 0)
+      {
+        len = ((w >> 27) & 0x7) + 11;
+        used += 5;
+      }
       else
       {
-        have -= 1;
-        window <<= 1;
-        if ((window & 0x80000000u) == 0)
-          k = 0;
-        else
+        len = ((w >> 22) & 0xFF) + 19;
+        used += 10;
+      }
+      // lzmh.c:560-568: `len` bytes from `back` bytes ago (128 for a zero offset out of the empty recent list); slots that
+      // were never written hold zero
+      const uint32_t back = off == 0 ? (uint32_t)kLzWindow : (uint32_t)off;
+      __syncwarp();
+      if (back >= 32)
+      {
+        uint32_t dst = rpos + lane;
+        if (lane < len)
+          sts_u8(ring + (dst & (kLzOutRing - 1)), lds_u8(ring + ((dst - back) & (kLzOutRing - 1))));
+#pragma unroll 1
+        for (uint32_t j0 = 32; j0 < len; j0 += 32)   // a trip reads bytes written before it began
         {
-          have -= 1;
-          window <<= 1;
-          if ((window & 0x80000000u) == 0)
-            k = 1;
-          else
+          __syncwarp();
+          dst += 32;
+          if (j0 + lane < len)
+            sts_u8(ring + (dst & (kLzOutRing - 1)), lds_u8(ring + ((dst - back) & (kLzOutRing - 1))));
+        }
+      }
+      else
+      {
+        // the copy may overlap itself: output byte j is byte j mod back of the `back` bytes before it, which no trip
+        // overwrites
+        uint32_t m = lds_u8(modtab + back * 32 + lane);
+        const uint32_t src = rpos - back;
+        uint32_t dst = rpos + lane;
+        if (lane < len)
+          sts_u8(ring + (dst & (kLzOutRing - 1)), lds_u8(ring + ((src + m) & (kLzOutRing - 1))));
+        if (len > 32)
+        {
+          const uint32_t step = lds_u8(modtab + 32 * 32 + back);
+#pragma unroll 1
+          for (uint32_t j0 = 32; j0 < len; j0 += 32)
           {
-            have -= 1;
-            window <<= 1;
-            k = (window & 0x80000000u) == 0 ? 2 : 3;
+            m += step;
+            m = m >= back ? m - back : m;
+            dst += 32;
+            if (j0 + lane < len)
+              sts_u8(ring + (dst & (kLzOutRing - 1)), lds_u8(ring + ((src + m) & (kLzOutRing - 1))));
           }
         }
-        have -= 1;
-        window <<= 1;
-        off = recent[k];
       }
-      for (; k > 0; k--)
-        recent[k] = recent[k - 1];
-      recent[0] = off;
-      if ((window & 0x80000000u) == 0)
-      {
-        len = (int)((window >> 28) & 0x7) + 3;
-        have -= 4;
-        window <<= 4;
-      }
-      else
-      {
-        have -= 1;
-        window <<= 1;
-        if ((window & 0x80000000u) == 0)
-        {
-          len = (int)((window >> 28) & 0x7) + 11;
-          have -= 4;
-          window <<= 4;
-        }
-        else
-        {
-          len = (int)((window >> 23) & 0xFF) + 19;
-          have -= 9;
-          window <<= 9;
-        }
-      }
-      for (int j = 0; j < len; j++)   // lzmh.c:560-568
-      {
-        // ring slot (hpos - off) mod 128: a byte written `off` back, the byte 128 back for off == 0, and a
-        // never-written (zero) slot when the stream is shorter than that
-        const uint64_t back = off == 0 ? (uint64_t)kLzWindow : (uint64_t)off;
-        uint8_t byte = 0;
-        if (back <= np && np - back < cap)
-          byte = out[np - back];
-        LZ_EMIT(byte);
-      }
+      __syncwarp();
+      rpos += len;
+      pend += len;
     }
-  } while (!r.eof() || window > 0);   // lzmh.c:571
-#undef LZ_EMIT
-  if (np > cap)
-    err = -6;
-  a.status[s] = err;
-  a.out_len[s] = err ? 0 : np;
+    rem -= (long long)used;
+    r.consume(used);
+    if (input_used_up && r.a_hi == 0)   // lzmh.c:571: reader at EOF and window empty
+      break;
+  }
+  while (pend)
+    flush(pend < kLzOutFlush ? pend : kLzOutFlush);
+  if (lane == 0)
+  {
+    const int err = flushed > cap ? -6 : 0;
+    a.status[s] = err;
+    a.out_len[s] = err ? 0 : flushed;
+  }
 }
+#endif   // !DC_HOST_SIM
 
 }  // namespace dc

@@ -1,7 +1,6 @@
 // lzmh_kernels.cu -- __global__ wrappers and launchers of the LZMH kernels (bodies: lzmh_device.cuh)
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "lzmh_device.cuh"
 
@@ -22,18 +21,25 @@ __global__ void __launch_bounds__(kLzEncWarps * 32) lzmh_encode_kernel(const Lzm
     lzmh_encode_warp(a, s, win[wid], lsym[wid], lcnt[wid]);
 }
 
-// The decoder is one sequential, branchy parse per block.  With 32 blocks per warp the lanes diverge (9 of 32 active
-// on average) and a 4096-block job is 128 warps on 148 SMs, i.e. bound by the latency of single warps.  So only the
-// first `lanes` lanes of every warp take a block: fewer lanes per warp = less divergence per warp and more warps to
-// hide latency with, at the price of more warp instructions in total.  The launcher picks `lanes` so that the job is
-// about one full wave of warps (model and measurements: profiles/r1_lzmh_lanes.txt).
-__global__ void __launch_bounds__(128) lzmh_decode_kernel(const LzmhArgs a, const uint32_t lanes)
+static const int kLzDecWarps = 4;
+
+__global__ void __launch_bounds__(kLzDecWarps * 32) lzmh_decode_kernel(const LzmhArgs a)
 {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t s = warp * lanes + lane;
-  if (lane < lanes && s < a.n_streams)
-    lzmh_decode_body(a, s);
+  __shared__ __align__(16) uint8_t ring[kLzDecWarps][kLzOutRing];
+  __shared__ __align__(4) uint8_t lsym[kLzDecWarps][kLzList];
+  __shared__ uint32_t lcnt[kLzDecWarps][kLzList];
+  __shared__ uint8_t modtab[kLzModTab];
+  for (uint32_t i = threadIdx.x; i < kLzModTab; i += blockDim.x)
+  {
+    const uint32_t back = i < 32 * 32 ? i >> 5 : i - 32 * 32, x = i < 32 * 32 ? i & 31 : 32;
+    modtab[i] = back ? (uint8_t)(x % back) : 0;
+  }
+  __syncthreads();
+  const int wid = threadIdx.x >> 5;
+  const uint64_t s = (uint64_t)blockIdx.x * kLzDecWarps + wid;
+  if (s < a.n_streams)
+    lzmh_decode_warp(a, s, (uint32_t)__cvta_generic_to_shared(ring[wid]), (uint32_t)__cvta_generic_to_shared(lsym[wid]),
+                     (uint32_t)__cvta_generic_to_shared(lcnt[wid]), (uint32_t)__cvta_generic_to_shared(modtab));
 }
 
 void launch_lzmh_encode(const LzmhArgs &a, cudaStream_t st)
@@ -49,18 +55,8 @@ void launch_lzmh_decode(const LzmhArgs &a, cudaStream_t st)
 {
   if (a.n_streams == 0)
     return;
-  // lanes per warp: a power of two such that the job is at most ~48 warps per SM (148 SMs)
-  uint32_t lanes = 1;
-  const char *force = getenv("DC_LZMH_DECODE_LANES");
-  if (force && atoi(force) >= 1 && atoi(force) <= 32)
-    lanes = (uint32_t)atoi(force);
-  else
-    while (lanes < 32 && (a.n_streams + lanes - 1) / lanes > 148ull * 48)
-      lanes *= 2;
-  const unsigned block = 128;
-  const uint64_t warps = (a.n_streams + lanes - 1) / lanes;
-  const unsigned grid = (unsigned)((warps * 32 + block - 1) / block);
-  lzmh_decode_kernel<<<grid, block, 0, st>>>(a, lanes);
+  const unsigned grid = (unsigned)((a.n_streams + kLzDecWarps - 1) / kLzDecWarps);
+  lzmh_decode_kernel<<<grid, kLzDecWarps * 32, 0, st>>>(a);
   count_launch(1);
 }
 

@@ -87,8 +87,6 @@ class Sim:
         L.sim_dega_decode_batch.restype = C.c_int
         L.sim_dega_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.sim_lzmh_decode.restype = C.c_int
-        L.sim_lzmh_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.sim_csv_encode.restype = C.c_uint64
         L.sim_csv_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_uint64]
         self.lib = L
@@ -112,13 +110,6 @@ class Sim:
                                     C.byref(ob))
         nb = int(ob.value) if rc == 0 else 0
         return rc, out[: (nb + 7) // 8].tobytes(), nb
-
-    def lzmh_decode(self, data, nbits, cap=1 << 20):
-        src = np.frombuffer(bytes(data), dtype=np.uint8)
-        out = np.zeros(cap, dtype=np.uint8)
-        n = C.c_uint64(0)
-        rc = self.lib.sim_lzmh_decode(src.ctypes.data if src.size else None, nbits, out.ctypes.data, cap, C.byref(n))
-        return rc, out[: n.value].tobytes(), int(n.value) * 8
 
     def dega_encode_batch(self, x, block_len, vs=32, nf=100.0, adaptive=1):
         x = np.ascontiguousarray(x, dtype=np.float32)

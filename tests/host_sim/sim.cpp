@@ -227,26 +227,6 @@ int sim_stage_run(int stage, const uint8_t *in, uint64_t in_bits, uint32_t vs, f
   }
 }
 
-// LZMH decode of one stream through the device body (the encoder is warp-cooperative and is tested on the GPU only)
-int sim_lzmh_decode(const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_len)
-{
-  std::vector<uint8_t> h_in((in_bits + 7) / 8 + 64, 0);
-  if (in_bits)
-    memcpy(h_in.data(), in, (in_bits + 7) / 8);
-  uint64_t nb = in_bits, off[2] = { 0, out_cap };
-  int32_t status = 0;
-  LzmhArgs la;
-  memset(&la, 0, sizeof(la));
-  la.n_streams = 1;
-  la.bits_in = BitSrc{ h_in.data(), nullptr, 0, &nb };
-  la.out = out;
-  la.out_off = off;
-  la.out_len = out_len;
-  la.status = &status;
-  lzmh_decode_body(la, 0);
-  return status;
-}
-
 // Batch DEGA encode over a uniform layout on host memory; writes per-stream payloads back to back (dense) the way
 // scan + gather do.  Returns 0 or the first negative code; status/bit_len/byte_off as in dc_dega_encode_device.
 int sim_dega_encode_batch(const float *samples, uint64_t n_channels, uint64_t channel_len, uint64_t block_len, uint32_t vs, float nf,

@@ -305,6 +305,22 @@ def test_lzmh_random_blocks_vs_oracle(ctx, oracle, seed):
         assert ctx.stage_run(ob.LZMH_DEC, got[1], got[2]) == oracle.run_chain([ob.LZMH_DEC], got[1], got[2]), (n, kind)
 
 
+def test_lzmh_decoder_on_arbitrary_bits(ctx, oracle):
+    """Streams no encoder wrote: random bits (every token kind, zero offsets out of the empty recent list, copies from
+    history that was never written, prefix codes that match nothing, tokens cut off by the end) and overlapping copies
+    of every period 1..40."""
+    rng = np.random.default_rng(77)
+    for n_bytes in (1, 2, 3, 8, 64, 300, 2000):
+        for _ in range(12):
+            junk = rng.integers(0, 256, n_bytes, dtype=np.uint8)
+            for nbits in (n_bytes * 8, n_bytes * 8 - 3):
+                assert ctx.stage_run(ob.LZMH_DEC, junk, nbits) == oracle.run_chain([ob.LZMH_DEC], junk, nbits, out_cap=1 << 20), (n_bytes, nbits)
+    for period in range(1, 41):
+        data = np.tile(rng.integers(0, 256, period, dtype=np.uint8), 700 // period + 1)[:700]
+        rc, enc, nb = oracle.run_chain([ob.LZMH_ENC], data, data.size * 8)
+        assert ctx.stage_run(ob.LZMH_DEC, enc, nb) == oracle.run_chain([ob.LZMH_DEC], enc, nb), period
+
+
 def test_lzmh_batch_blocks(ctx, oracle):
     from data_compressor_b200 import synth
     data = synth.watts_u16(24, 32768 + 100, device="cuda").reshape(-1)       # 64 KiB blocks + a ragged tail

@@ -151,26 +151,6 @@ def test_batch_failed_stream_is_isolated(sim, oracle):
     assert payload[int(byte_off[2]):].tobytes() == oracle.dega_encode(x[2])[1]
 
 
-def test_lzmh_decoder_body_vs_golden_and_oracle(sim, oracle, golden):
-    for name in golden.names:
-        g = golden.get(name)
-        if g["chain"] != [ob.LZMH_DEC]:
-            continue
-        rc, out, nb = sim.lzmh_decode(g["input"].tobytes(), g["in_bits"])
-        assert rc == g["rc"] and nb == g["out_bits"], name
-        assert out == g["out"].tobytes(), name
-    rng = np.random.default_rng(11)
-    for n in (0, 1, 5, 403, 404, 3000):
-        data = rng.integers(0, 6, n, dtype=np.uint8)
-        rc, enc, nb = oracle.run_chain([ob.LZMH_ENC], data, n * 8)
-        want = oracle.run_chain([ob.LZMH_DEC], enc, nb)
-        assert sim.lzmh_decode(enc, nb) == want
-        junk = rng.integers(0, 256, 64, dtype=np.uint8)
-        a = sim.lzmh_decode(junk.tobytes(), 512, cap=1 << 16)
-        b = oracle.run_chain([ob.LZMH_DEC], junk, 512, out_cap=1 << 16)
-        assert a == b
-
-
 @pytest.mark.parametrize("adaptive", [0, 1])
 def test_bac_carry_through_stored_words(sim, oracle, adaptive):
     """Pending runs of 30..300 bits resolved upwards and downwards: the encoder's carry has to ripple through its
