@@ -72,11 +72,52 @@ __device__ __forceinline__ void lz_token(int k, int off, int len, uint32_t &code
 static const int kLzWin = 1024;   // bytes of the stream kept in shared memory per warp
 static const int kLzWinPad = 16;  // readable slack behind the window (word-wise match compare)
 
+// shared memory through 32-bit addresses (the generic-pointer form recomputes the window base in the token loop)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // four bytes starting at byte `idx` of a 4-byte aligned shared-memory array, first byte in the low bits
 __device__ __forceinline__ uint32_t lz_load32(const uint8_t *base, uint32_t idx)
 {
   const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (idx >> 2);
   return __funnelshift_r(w[0], w[1], (idx & 3) * 8);
+}
+
+// win[0 .. kLzWin) <- src[wbase ..), as far as the stream goes: whole words when the source is aligned (eight loads in
+// flight per lane), bytes otherwise and for the last few
+__device__ __forceinline__ void lz_fill_window(uint8_t *win, const uint8_t *src, uint32_t wbase, uint32_t n, uint32_t lane)
+{
+  const uint32_t avail = n - wbase < (uint32_t)kLzWin ? n - wbase : (uint32_t)kLzWin;
+  uint32_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(src + wbase) & 3) == 0)
+  {
+    const uint32_t nw = avail >> 2;
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src + wbase);
+    uint32_t *w32 = reinterpret_cast<uint32_t *>(win);
+    uint32_t v[kLzWin / 128];
+#pragma unroll
+    for (int k = 0; k < kLzWin / 128; k++)
+      v[k] = lane + 32 * k < nw ? __ldg(s32 + lane + 32 * k) : 0u;
+#pragma unroll
+    for (int k = 0; k < kLzWin / 128; k++)
+      if (lane + 32 * k < nw)
+        w32[lane + 32 * k] = v[k];
+    done = nw << 2;
+  }
+  for (uint32_t i = done + lane; i < avail; i += 32)
+    win[i] = src[wbase + i];
 }
 
 __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uint8_t *win, uint8_t *lsym, uint32_t *lcnt)
@@ -86,14 +127,14 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
   const uint32_t n = (uint32_t)(a.in_off[s + 1] - a.in_off[s]);
   BitWriter w;
   w.init(dst_ptr(a.bits_out, s), a.bits_out.stride_bytes);
+  const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
 
   if (n != (uint32_t)kLzRing)   // lzmh.c:169-173: the initial fill of exactly 403 bytes wraps write == read at EOF
   {
     int recent0 = 0, recent1 = 0, recent2 = 0, recent3 = 0;   // lzmh.c:157-159
     uint32_t nlist = 0;
     uint32_t wbase = 0;
-    for (uint32_t i = lane; i < kLzWin && i < n; i += 32)
-      win[i] = src[i];
+    lz_fill_window(win, src, 0, n, lane);
     __syncwarp();
     uint32_t pos = 0;
     while (pos < n)   // lzmh.c:173
@@ -101,52 +142,70 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
       if (pos + kLzMaxLen > wbase + kLzWin && wbase + kLzWin < n)   // slide the window: keep 128 bytes of history
       {
         __syncwarp();
-        wbase = pos - kLzWindow;
-        for (uint32_t i = lane; i < kLzWin && wbase + i < n; i += 32)
-          win[i] = src[wbase + i];
+        wbase = (pos - kLzWindow) & ~3u;   // word steps keep the alignment of the stream
+        lz_fill_window(win, src, wbase, n, lane);
         __syncwarp();
       }
       const uint32_t p = pos - wbase;
       const int maxoff = pos < (uint32_t)kLzWindow ? (int)pos : kLzWindow;            // lzmh.c:175-179
       const int maxlen = n - pos > (uint32_t)kLzMaxLen ? kLzMaxLen : (int)(n - pos);   // lzmh.c:180-190
-      // ---- match search (lzmh.c:192-214): 4 offsets per lane, ascending, strictly longer wins
+      // ---- match search (lzmh.c:192-214): 4 offsets per lane (lane + 1 + 32 j), ascending, strictly longer wins
       uint32_t key = 0;   // (length << 8) | (255 - offset): max = longest, then smallest offset
       const uint8_t c0 = win[p];
-      const uint32_t w0 = lz_load32(win, p);   // the four bytes at the parse position (same for every lane: a broadcast)
+      const uint32_t sp = (p & 3) * 8, wp = win_s + (p & ~3u);
+      // the twelve bytes at the parse position (the same for every lane: broadcasts)
+      const uint32_t t0 = lds_u32(wp), t1 = lds_u32(wp + 4), t2 = lds_u32(wp + 8), t3 = lds_u32(wp + 12);
+      const uint32_t w0 = __funnelshift_r(t0, t1, sp), w1 = __funnelshift_r(t1, t2, sp), w2 = __funnelshift_r(t2, t3, sp);
+      // Only matches of three bytes or more count (lzmh.c:216), so the first test is on the first word of all four
+      // candidates, for all lanes in step: their addresses differ by 32 bytes, so one alignment serves the four.
+      const uint32_t cbase = p - lane - 1;                                  // candidate j starts 32 j bytes before this
+      const uint32_t sc = (cbase & 3) * 8, wc = win_s + (cbase & ~3u);
+      const int nval = maxoff > (int)lane ? ((maxoff - (int)lane - 1) >> 5) + 1 : 0;   // candidates of this lane within maxoff
+      uint32_t pending = 0;   // candidates whose first four bytes match: their length is still open
 #pragma unroll
       for (int j = 0; j < 4; j++)
-      {
-        const int off = (int)lane + 1 + 32 * j;
-        if (off <= maxoff)
+        if (j < nval)
         {
-          // Only matches of three bytes or more count (lzmh.c:216), so the first test is on three bytes at once and
-          // runs for all lanes in step; the extension loop -- four bytes per trip, unaligned reads assembled from
-          // aligned words, whatever is read past maxlen cut off below -- is left to the few candidates that matched
-          // four bytes already.
-          uint32_t x = lz_load32(win, p - off) ^ w0;
-          if ((x & 0x00FFFFFFu) == 0)
+          const uint32_t x = __funnelshift_r(lds_u32(wc - 32 * j), lds_u32(wc - 32 * j + 4), sc) ^ w0;
+          if (x == 0)
+            pending |= 1u << j;
+          else if ((x & 0x00FFFFFFu) == 0 && maxlen >= 3)
+            key = max(key, (3u << 8) | (uint32_t)(255 - ((int)lane + 1 + 32 * j)));
+        }
+      // The few candidates that matched four bytes are extended, one per lane at a time: the next eight bytes against
+      // registers, anything longer four bytes per trip; whatever is read past maxlen is cut off.
+      while (pending)
+      {
+        const int j = __ffs((int)pending) - 1;
+        pending &= pending - 1;
+        const uint32_t wj = wc - 32 * j;
+        int len;
+        uint32_t x = __funnelshift_r(lds_u32(wj + 4), lds_u32(wj + 8), sc) ^ w1;
+        if (x != 0)
+          len = 4 + ((__ffs((int)x) - 1) >> 3);
+        else
+        {
+          x = __funnelshift_r(lds_u32(wj + 8), lds_u32(wj + 12), sc) ^ w2;
+          if (x != 0)
+            len = 8 + ((__ffs((int)x) - 1) >> 3);
+          else
           {
-            int len = 3;
-            if (x == 0)
+            len = 12;
+            while (len < maxlen)
             {
-              len = 4;
-              while (len < maxlen)
+              x = __funnelshift_r(lds_u32(wj + len), lds_u32(wj + len + 4), sc) ^ __funnelshift_r(lds_u32(wp + len), lds_u32(wp + len + 4), sp);
+              if (x != 0)
               {
-                x = lz_load32(win, p - off + len) ^ lz_load32(win, p + len);
-                if (x != 0)
-                {
-                  len += (__ffs((int)x) - 1) >> 3;
-                  break;
-                }
-                len += 4;
+                len += (__ffs((int)x) - 1) >> 3;
+                break;
               }
+              len += 4;
             }
-            len = len < maxlen ? len : maxlen;
-            const uint32_t k2 = ((uint32_t)len << 8) | (uint32_t)(255 - off);
-            if (len >= 3 && k2 > key)
-              key = k2;
           }
         }
+        len = len < maxlen ? len : maxlen;
+        if (len >= 3)
+          key = max(key, ((uint32_t)len << 8) | (uint32_t)(255 - ((int)lane + 1 + 32 * j)));
       }
       key = __reduce_max_sync(0xFFFFFFFFu, key);
       uint32_t code, nbits;
@@ -253,22 +312,6 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
 static const uint32_t kLzOutRing = 1024;    // bytes of output kept in shared memory per warp (power of two)
 static const uint32_t kLzOutFlush = 512;    // bytes per flush
 static const uint32_t kLzModTab = 32 * 32 + 32;   // [back][lane] = lane % back for back < 32, then [back] = 32 % back
-
-// shared memory through 32-bit addresses (the generic-pointer form recomputes the window base in the token loop)
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 struct LzWarpBits   // warp-uniform MSB-first bit source
 {
