@@ -156,36 +156,17 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
       // the twelve bytes at the parse position (the same for every lane: broadcasts)
       const uint32_t t0 = lds_u32(wp), t1 = lds_u32(wp + 4), t2 = lds_u32(wp + 8), t3 = lds_u32(wp + 12);
       const uint32_t w0 = __funnelshift_r(t0, t1, sp), w1 = __funnelshift_r(t1, t2, sp), w2 = __funnelshift_r(t2, t3, sp);
-      // Only matches of three bytes or more count (lzmh.c:216), so the first test is on the first word of all four
-      // candidates, for all lanes in step: their addresses differ by 32 bytes, so one alignment serves the four.
-      const uint32_t cbase = p - lane - 1;                                  // candidate j starts 32 j bytes before this
-      const uint32_t sc = (cbase & 3) * 8, wc = win_s + (cbase & ~3u);
-      const int nval = maxoff > (int)lane ? ((maxoff - (int)lane - 1) >> 5) + 1 : 0;   // candidates of this lane within maxoff
-      uint32_t pending = 0;   // candidates whose first four bytes match: their length is still open
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (j < nval)
-        {
-          const uint32_t x = __funnelshift_r(lds_u32(wc - 32 * j), lds_u32(wc - 32 * j + 4), sc) ^ w0;
-          if (x == 0)
-            pending |= 1u << j;
-          else if ((x & 0x00FFFFFFu) == 0 && maxlen >= 3)
-            key = max(key, (3u << 8) | (uint32_t)(255 - ((int)lane + 1 + 32 * j)));
-        }
-      // The few candidates that matched four bytes are extended, one per lane at a time: the next eight bytes against
-      // registers, anything longer four bytes per trip; whatever is read past maxlen is cut off.
-      while (pending)
-      {
-        const int j = __ffs((int)pending) - 1;
-        pending &= pending - 1;
-        const uint32_t wj = wc - 32 * j;
+      // A candidate that matched its first four bytes is extended: the next eight bytes against registers, anything
+      // longer four bytes per trip; whatever is read past maxlen is cut off.  `wq` / `sq`: word address and alignment
+      // shift of the candidate's first byte.
+      auto extend = [&](const uint32_t wq, const uint32_t sq, const uint32_t off) {
         int len;
-        uint32_t x = __funnelshift_r(lds_u32(wj + 4), lds_u32(wj + 8), sc) ^ w1;
+        uint32_t x = __funnelshift_r(lds_u32(wq + 4), lds_u32(wq + 8), sq) ^ w1;
         if (x != 0)
           len = 4 + ((__ffs((int)x) - 1) >> 3);
         else
         {
-          x = __funnelshift_r(lds_u32(wj + 8), lds_u32(wj + 12), sc) ^ w2;
+          x = __funnelshift_r(lds_u32(wq + 8), lds_u32(wq + 12), sq) ^ w2;
           if (x != 0)
             len = 8 + ((__ffs((int)x) - 1) >> 3);
           else
@@ -193,7 +174,7 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
             len = 12;
             while (len < maxlen)
             {
-              x = __funnelshift_r(lds_u32(wj + len), lds_u32(wj + len + 4), sc) ^ __funnelshift_r(lds_u32(wp + len), lds_u32(wp + len + 4), sp);
+              x = __funnelshift_r(lds_u32(wq + len), lds_u32(wq + len + 4), sq) ^ __funnelshift_r(lds_u32(wp + len), lds_u32(wp + len + 4), sp);
               if (x != 0)
               {
                 len += (__ffs((int)x) - 1) >> 3;
@@ -205,7 +186,52 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
         }
         len = len < maxlen ? len : maxlen;
         if (len >= 3)
-          key = max(key, ((uint32_t)len << 8) | (uint32_t)(255 - ((int)lane + 1 + 32 * j)));
+          key = max(key, ((uint32_t)len << 8) | (255u - off));
+      };
+      // Only matches of three bytes or more count (lzmh.c:216), so the first test is on the first word of every
+      // candidate, for all lanes in step; the few that match all four bytes are extended afterwards, one per lane at a time.
+      if (maxoff == kLzWindow)
+      {
+        // 128 bytes of history (all but the first steps of a stream).  Lane l takes the four candidates that start in
+        // the word at p - 128 + 4 l, i.e. the offsets 128 - 4 l - k: three aligned words, shifted like the bytes at p,
+        // hold all four first words.
+        const uint32_t qa = wp - kLzWindow + 4 * lane;
+        const uint32_t a0 = lds_u32(qa), a1 = lds_u32(qa + 4), a2 = lds_u32(qa + 8);
+        const uint32_t d0 = __funnelshift_r(a0, a1, sp), d1 = __funnelshift_r(a1, a2, sp);
+        const uint32_t x0 = d0 ^ w0, x1 = __funnelshift_r(d0, d1, 8) ^ w0, x2 = __funnelshift_r(d0, d1, 16) ^ w0,
+                       x3 = __funnelshift_r(d0, d1, 24) ^ w0;
+        uint32_t pending = 0;
+        if (maxlen >= 3)
+        {
+          const uint32_t kb = (3u << 8) | (127u + 4 * lane);   // 255 - offset of candidate 0; the later ones are nearer
+          key = (x0 & 0x00FFFFFFu) == 0 ? kb : 0u;
+          key = (x1 & 0x00FFFFFFu) == 0 ? kb + 1 : key;
+          key = (x2 & 0x00FFFFFFu) == 0 ? kb + 2 : key;
+          key = (x3 & 0x00FFFFFFu) == 0 ? kb + 3 : key;
+          pending = (x0 == 0 ? 1u : 0u) | (x1 == 0 ? 2u : 0u) | (x2 == 0 ? 4u : 0u) | (x3 == 0 ? 8u : 0u);
+        }
+        while (pending)
+        {
+          const uint32_t k = (uint32_t)__ffs((int)pending) - 1;
+          pending &= pending - 1;
+          const uint32_t q = p - kLzWindow + 4 * lane + k;
+          extend(win_s + (q & ~3u), (q & 3) * 8, (uint32_t)kLzWindow - 4 * lane - k);
+        }
+      }
+      else
+      {
+        // the first 128 bytes of a stream: offsets lane + 1 + 32 j as far as the history goes
+        const uint32_t cbase = p - lane - 1;
+        const uint32_t sc = (cbase & 3) * 8, wc = win_s + (cbase & ~3u);
+        const int nval = maxoff > (int)lane ? ((maxoff - (int)lane - 1) >> 5) + 1 : 0;
+        for (int j = 0; j < nval; j++)
+        {
+          const uint32_t x = __funnelshift_r(lds_u32(wc - 32 * j), lds_u32(wc - 32 * j + 4), sc) ^ w0;
+          if (x == 0)
+            extend(wc - 32 * j, sc, lane + 1 + 32 * j);
+          else if ((x & 0x00FFFFFFu) == 0 && maxlen >= 3)
+            key = max(key, (3u << 8) | (254u - lane - 32 * j));
+        }
       }
       key = __reduce_max_sync(0xFFFFFFFFu, key);
       uint32_t code, nbits;
