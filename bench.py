@@ -13,6 +13,7 @@ step through the host-buffer C ABI (dc_dega_encode_host / dc_dega_decode_host) w
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -282,13 +283,17 @@ def run_ours(args):
     t_wait = time.time()
     while sampler.is_alive() and not sampler.rows and time.time() - t_wait < 5.0:   # NVML initialisation stays out of the timed region
         time.sleep(0.05)
-    for _ in range(2):
+    gc.collect()
+    gc.disable()   # a generation-2 collection with torch loaded takes ~50 ms: keep it out of a 14 ms step (as timeit does)
+    for _ in range(2):   # no idle gap between the last warm-up step and the timed region
         step()
-    barrier()
-    launches0 = ctx.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for ev in [ev0, ev1] + step_ev:   # torch creates the CUDA event at its first record: do that outside the timed region
+        ev.record(ctx.stream)
+    barrier()
+    launches0 = ctx.launch_count()
     kernel_ms = {}
     t_enc = t_dec = 0.0
     with torch.cuda.stream(ctx.stream):
@@ -309,6 +314,7 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
+    gc.enable()
     sampler.stop()
     ctx.set_profiling(False)
     ok = bool(torch.equal(y.view(torch.int32), x.view(torch.int32))) and not bool(enc.status.any().item())
@@ -335,12 +341,15 @@ def run_ours(args):
             pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
             yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
         barrier()
+        gc.collect()
+        gc.disable()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
             yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
         barrier()
         dt = (time.perf_counter() - t0) / e2e_steps
+        gc.enable()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -400,7 +409,7 @@ def run_ours(args):
         "compression_ratio": world * raw_bytes / float(tot_bytes.item()),
         "encode_ms": sum(kernel_ms.get(k, 0.0) for k in ("front", "bac_encode", "scan", "gather")),
         "decode_ms": sum(kernel_ms.get(k, 0.0) for k in ("bac_decode", "back")),
-        "kernel_ms": kernel_ms, "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)], "round_trip_ok": ok,
+        "kernel_ms": kernel_ms, "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)], "slowest_step": step_ms.index(max(step_ms)), "round_trip_ok": ok,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
