@@ -94,6 +94,7 @@ SYMBOLS = {
     "dc_container_read_index": (_I, [C.c_char_p, _PH, _U64, _U64, _P]),
     "dc_container_read_payload": (_I, [C.c_char_p, _PH, _U64, _U64, _P]),
     "dc_stage_run_host": (_I, [_P, _I, _P, _U64, _PP, _P, _U64, _PU64]),
+    "dc_chain_run_host": (_I, [_P, C.c_uint32, C.POINTER(_I), _PP, _P, _U64, _P, _U64, _PU64, C.POINTER(C.c_uint32)]),
     "dc_stage_out_bound": (_U64, [_I, _U64, _PP]),
 }
 

@@ -322,3 +322,28 @@ class Context:
             break
         nb = int(out_bits.value) if rc == 0 else 0
         return rc, out[: (nb + 7) // 8].tobytes(), nb
+
+    def chain_run(self, stages, data, nbits: int | None = None, vs: int = 32, nf: float = 100.0, adaptive: bool = False,
+                  out_cap: int | None = None):
+        """`encode X # encode Y # ...` over one stream with the intermediate results kept on the device
+        (dc_chain_run_host).  `stages` is a list of stage numbers; the options apply to every stage, as when the
+        command line repeats them.  Returns (code, bytes, nbits, failed_stage)."""
+        src = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        if nbits is None:
+            nbits = src.size * 8
+        n = len(stages)
+        st = (C.c_int * n)(*[int(x) for x in stages])
+        pars = (Params * n)(*[self._params(vs, nf, adaptive) for _ in range(n)])
+        cap = out_cap or max(1 << 16, src.size * 40 + 4096)
+        out_bits, failed = C.c_uint64(0), C.c_uint32(0)
+        for _ in range(3):
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self.lib.dc_chain_run_host(self.h, n, st, pars, src.ctypes.data if src.size else None, nbits, out.ctypes.data, out.size,
+                                            C.byref(out_bits), C.byref(failed))
+            if rc == _lib.ERR_MEMORY and out_bits.value and (out_bits.value + 7) // 8 > out.size:
+                cap = (out_bits.value + 7) // 8 + 16
+                continue
+            break
+        nb = int(out_bits.value) if rc == 0 else 0
+        return rc, out[: (nb + 7) // 8].tobytes(), nb, int(failed.value)

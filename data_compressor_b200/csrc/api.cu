@@ -29,6 +29,8 @@ struct dc_ctx
   uint64_t arena_size;
   uint8_t *stage;        // device staging of the host-buffer calls (samples, payload, index), grown on demand
   uint64_t stage_size;
+  uint8_t *chain[2];     // intermediate results of dc_chain_run_host (ping-pong), grown on demand
+  uint64_t chain_size[2];
   cudaStream_t s_h2d, s_d2h;          // copy engines of the host-buffer calls (overlap with the compute stream)
   cudaEvent_t ev_in[kMaxHostChunks], ev_out[kMaxHostChunks];    // per-chunk "input landed" / "results ready"
   uint64_t *h_pinned;   // small pinned mailbox for device->host scalars
@@ -117,6 +119,9 @@ int stage_reserve(dc_ctx *c, uint64_t bytes)
   CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
   if (c->stage)
     cudaFree(c->stage);
+  for (int i = 0; i < 2; i++)
+    if (c->chain[i])
+      cudaFree(c->chain[i]);
   c->stage = nullptr;
   c->stage_size = 0;
   const uint64_t want = round_up(bytes, 1 << 20);
@@ -1242,7 +1247,8 @@ int dc_lzmh_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_
 }
 
 // one LZMH stage over one host stream (plugin face)
-static int lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_bits)
+static int lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, cudaMemcpyKind in_kind, uint64_t in_bits, uint8_t *out, cudaMemcpyKind out_kind,
+                           uint64_t out_cap, uint64_t *out_bits)
 {
   const uint64_t in_bytes = (in_bits + 7) / 8;
   if (encode && (in_bits & 7))
@@ -1261,7 +1267,7 @@ static int lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in
     CU_TRY(c, cudaMemcpyAsync(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
     CU_TRY(c, cudaMemsetAsync(d_in + (in_bytes & ~(uint64_t)15), 0, 32, c->stream), DC_ERR_LIBRARY_CALL);
     if (in_bytes)
-      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, in_kind, c->stream), DC_ERR_LIBRARY_CALL);
     LzmhArgs la;
     memset(&la, 0, sizeof(la));
     la.n_streams = 1;
@@ -1303,7 +1309,7 @@ static int lzmh_stage_host(dc_ctx *c, int encode, const uint8_t *in, uint64_t in
       return DC_ERR_MEMORY;
     if (nbytes)
     {
-      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, out_kind, c->stream), DC_ERR_LIBRARY_CALL);
       CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
     }
     return DC_OK;
@@ -1332,15 +1338,17 @@ uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *p)
   }
 }
 
-int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits, const dc_params *params, uint8_t *out, uint64_t out_cap,
-                      uint64_t *out_bits)
+// One stage over one stream.  `in` / `out` are host or device buffers as the copy kinds say (device for the inner stages
+// of dc_chain_run_host).
+static int stage_run(dc_ctx *c, int stage, const uint8_t *in, cudaMemcpyKind in_kind, uint64_t in_bits, const dc_params *params, uint8_t *out,
+                     cudaMemcpyKind out_kind, uint64_t out_cap, uint64_t *out_bits)
 {
   if (!c || !params_ok(params) || !out_bits || stage < 0 || stage >= DC_STAGE_COUNT)
     return DC_ERR_INVALID_VALUE;
   *out_bits = 0;
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
   if (stage == DC_STAGE_LZMH_ENC || stage == DC_STAGE_LZMH_DEC)
-    return lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_bits, out, out_cap, out_bits);
+    return lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_kind, in_bits, out, out_kind, out_cap, out_bits);
 
   const uint32_t vs = params->value_size_bits;
   const uint64_t in_bytes = (in_bits + 7) / 8;
@@ -1399,7 +1407,7 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
     CU_TRY(c, cudaMemsetAsync(d_meta, 0, 8 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
     CU_TRY(c, cudaMemsetAsync(d_in + (in_bytes & ~(uint64_t)15), 0, 32, c->stream), DC_ERR_LIBRARY_CALL);
     if (in_bytes)
-      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpyAsync(d_in, in, in_bytes, in_kind, c->stream), DC_ERR_LIBRARY_CALL);
     CU_TRY(c, cudaMemcpyAsync(d_meta, &in_bits, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
 
     BitSrc src_in;
@@ -1526,11 +1534,72 @@ int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits,
     }
     if (nbytes)
     {
-      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, cudaMemcpyDeviceToHost, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaMemcpyAsync(out, d_out, nbytes, out_kind, c->stream), DC_ERR_LIBRARY_CALL);
       CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
     }
     return DC_OK;
   }
+}
+
+int dc_stage_run_host(dc_ctx *c, int stage, const uint8_t *in, uint64_t in_bits, const dc_params *params, uint8_t *out, uint64_t out_cap,
+                      uint64_t *out_bits)
+{
+  return stage_run(c, stage, in, cudaMemcpyHostToDevice, in_bits, params, out, cudaMemcpyDeviceToHost, out_cap, out_bits);
+}
+
+// ---- chains: `encode X # encode Y # ...` with the intermediate results kept on the device ---------------------
+static int chain_reserve(dc_ctx *c, int which, uint64_t bytes)
+{
+  if (bytes <= c->chain_size[which])
+    return DC_OK;
+  if (c->chain[which])
+    cudaFree(c->chain[which]);
+  c->chain[which] = nullptr;
+  c->chain_size[which] = 0;
+  const uint64_t want = round_up(bytes + bytes / 4 + 4096, 4096);
+  CU_TRY(c, cudaMalloc(&c->chain[which], want), DC_ERR_MEMORY);
+  c->chain_size[which] = want;
+  return DC_OK;
+}
+
+int dc_chain_run_host(dc_ctx *c, uint32_t n_stages, const int *stages, const dc_params *params, const uint8_t *in, uint64_t in_bits, uint8_t *out,
+                      uint64_t out_cap, uint64_t *out_bits, uint32_t *failed_stage)
+{
+  if (!c || n_stages == 0 || n_stages > 16 || !stages || !params || !out_bits)   // 16 = MAX_NUM_ENCODERS, DCCLI/inc/params.h:10
+    return DC_ERR_INVALID_VALUE;
+  *out_bits = 0;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  const uint8_t *cur = in;
+  uint64_t bits = in_bits;
+  for (uint32_t i = 0; i < n_stages; i++)
+  {
+    if (failed_stage)
+      *failed_stage = i;
+    const bool first = i == 0, last = i + 1 == n_stages;
+    if (last)
+      return stage_run(c, stages[i], cur, first ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, bits, &params[i], out, cudaMemcpyDeviceToHost,
+                       out_cap, out_bits);
+    // an inner stage writes into the ping-pong buffer the next one reads; the decoders' sizes are only known afterwards,
+    // so a result that did not fit reports its size and the stage runs once more
+    const int which = (int)(i & 1);
+    uint64_t need = dc_stage_out_bound(stages[i], bits, &params[i]), got = 0;
+    int rc = DC_OK;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+      if ((rc = chain_reserve(c, which, need)) != DC_OK)
+        return rc;
+      rc = stage_run(c, stages[i], cur, first ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, bits, &params[i], c->chain[which],
+                     cudaMemcpyDeviceToDevice, c->chain_size[which], &got);
+      if (rc != DC_ERR_MEMORY || (got + 7) / 8 <= c->chain_size[which])
+        break;
+      need = (got + 7) / 8;
+    }
+    if (rc != DC_OK)
+      return rc;
+    cur = c->chain[which];
+    bits = got;
+  }
+  return DC_OK;
 }
 
 }  // extern "C"

@@ -257,6 +257,15 @@ enum dc_stage
    needed.  On a codec error (negative return) *out_bits is 0. */
 int dc_stage_run_host(dc_ctx *ctx, int stage, const uint8_t *in, uint64_t in_bits, const dc_params *params,
                       uint8_t *out, uint64_t out_cap, uint64_t *out_bits);
+
+/* A chain of stages over one stream, `encode X # encode Y # ...` of the reference's command line (DCCLI/src/cli.c:430-466
+   runs the stages one after the other, each reading what the one before wrote).  The intermediate results stay in device
+   memory: one copy in, one copy out.  stages[i] is a DC_STAGE_* value, params[i] its options (the reference parses
+   options per stage, DCCLI/src/params.c:248); at most 16 stages (DCCLI/inc/params.h:10).  Returns the code of the first
+   stage that fails -- *failed_stage (may be NULL) then holds its index -- with the reference's meaning.  On DC_ERR_MEMORY
+   from the last stage *out_bits holds the size that would have been needed. */
+int dc_chain_run_host(dc_ctx *ctx, uint32_t n_stages, const int *stages, const dc_params *params, const uint8_t *in,
+                      uint64_t in_bits, uint8_t *out, uint64_t out_cap, uint64_t *out_bits, uint32_t *failed_stage);
 /* Upper bound, in bytes, of the output of `stage` for an input of in_bits bits. */
 uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *params);
 

@@ -509,3 +509,53 @@ def test_csv_decode_many_strtof_fields(ctx, oracle):
     text = "".join(f"{v}e-2\n" if i % 2 else f"{v / 100:.2f}\n" for i, v in enumerate(vals))
     got, want = ctx.csv_decode(text), oracle.csv_decode(text)
     assert got.size == vals.size and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- chains with the intermediate results on the device ------------------------------------------
+@pytest.mark.parametrize("vs,adaptive", [(32, True), (24, False), (17, True), (64, True)])
+def test_chain_run_matches_oracle_chain(ctx, oracle, golden, vs, adaptive):
+    """dc_chain_run_host over the reference's command lines: the DEGA chain stage by stage and its inverse, partial chains,
+    a chain that ends in lzmh, and the same chains cut after every stage (the intermediate results of a DCCLI run)."""
+    x = golden.testfile[:20000]
+    enc = [ob.NORMALIZE, ob.DIFF_ENC, ob.SEG_ENC, ob.BAC_ENC]
+    dec = [ob.BAC_DEC, ob.SEG_DEC, ob.DIFF_DEC, ob.DENORMALIZE]
+    for k in range(1, 5):
+        want = oracle.run_chain(enc[:k], x, x.size * 32, vs=vs, adaptive=adaptive)
+        got = ctx.chain_run(enc[:k], x, x.size * 32, vs=vs, adaptive=adaptive)
+        assert got[:3] == want, (k, got[0], want[0])
+    rc, payload, nb = oracle.run_chain(enc, x, x.size * 32, vs=vs, adaptive=adaptive)
+    for k in range(1, 5):
+        want = oracle.run_chain(dec[:k], payload, nb, vs=vs, adaptive=adaptive, out_cap=1 << 22)
+        got = ctx.chain_run(dec[:k], payload, nb, vs=vs, adaptive=adaptive)
+        assert got[:3] == want, (k, got[0], want[0])
+    # eight stages: there and back in one call
+    rc, back, nb2, _ = ctx.chain_run(enc + dec, x, x.size * 32, vs=vs, adaptive=adaptive)
+    assert rc == 0 and nb2 == x.size * 32 and back == oracle.run_chain(enc + dec, x, x.size * 32, vs=vs, adaptive=adaptive, out_cap=1 << 22)[1]
+    if vs == 32:
+        assert np.array_equal(np.frombuffer(back, dtype=np.uint32), x.view(np.uint32))
+        mixed = [ob.NORMALIZE, ob.DIFF_ENC, ob.LZMH_ENC]
+        assert ctx.chain_run(mixed, x, x.size * 32)[:3] == oracle.run_chain(mixed, x, x.size * 32)
+        assert ctx.chain_run(mixed + [ob.LZMH_DEC, ob.DIFF_DEC], x, x.size * 32)[:3] == \
+            oracle.run_chain(mixed + [ob.LZMH_DEC, ob.DIFF_DEC], x, x.size * 32, out_cap=1 << 22)
+
+
+def test_chain_run_errors_and_edges(ctx, oracle):
+    """The chain stops at the stage the reference would stop at, with its code; empty input; one stage; too many stages."""
+    x = np.array([1.0, -2.5, 3.0], dtype=np.float32)            # a negative sample: diff refuses it (diff.c:17-18)
+    chain = [ob.NORMALIZE, ob.DIFF_ENC, ob.SEG_ENC, ob.BAC_ENC]
+    rc, out, nb, failed = ctx.chain_run(chain, x, 96)
+    want = oracle.run_chain(chain, x, 96)
+    assert rc == want[0] != 0 and failed == 1 and nb == 0
+    big = np.array([3e9], dtype=np.float32)                      # out of range for valuesize 32: normalize refuses it
+    rc, out, nb, failed = ctx.chain_run(chain, big, 32)
+    assert rc == oracle.run_chain(chain, big, 32)[0] != 0 and failed == 0
+    empty = np.zeros(0, dtype=np.float32)
+    assert ctx.chain_run(chain, empty, 0)[:3] == oracle.run_chain(chain, empty, 0)
+    assert ctx.chain_run([ob.SEG_ENC], np.arange(5, dtype=np.uint32), 160)[:3] == oracle.run_chain([ob.SEG_ENC], np.arange(5, dtype=np.uint32), 160)
+    assert ctx.chain_run([ob.NORMALIZE] * 17, x, 96)[0] == -1    # ERROR_INVALID_VALUE: more than MAX_NUM_ENCODERS stages
+    # a decoder chain whose first result is far larger than its input (the buffer between the stages has to grow)
+    zeros = np.zeros(300000, dtype=np.float32)
+    rc, payload, nb = oracle.run_chain(chain, zeros, zeros.size * 32, adaptive=True)
+    dec = [ob.BAC_DEC, ob.SEG_DEC, ob.DIFF_DEC, ob.DENORMALIZE]
+    got = ctx.chain_run(dec, payload, nb, adaptive=True)
+    assert got[0] == 0 and got[2] == zeros.size * 32 and not np.frombuffer(got[1], dtype=np.uint32).any()
