@@ -285,8 +285,10 @@ def run_ours(args):
         time.sleep(0.05)
     gc.collect()
     gc.disable()   # a generation-2 collection with torch loaded takes ~50 ms: keep it out of a 14 ms step (as timeit does)
-    for _ in range(2):   # no idle gap between the last warm-up step and the timed region
-        step()
+    with torch.cuda.stream(ctx.stream):   # torch's caching allocator keeps one pool per stream: the wrapper's small result tensors
+        for _ in range(2):                # must come out of the pool of the stream the timed region runs under, not out of cudaMalloc
+            step()                        # (seen as a 10-150 ms first decode call); otherwise exactly what a timed step does
+            ctx.kernel_ms()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -379,7 +381,20 @@ def run_ours(args):
             traffic = tj.get(dom + "_kernel")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    issue = None
+    try:   # what actually bounds the coder: warp instructions per launch (ncu, same shape) against one per cycle per scheduler
+        wi = tj["warp_instructions"][dom + "_kernel"] if traffic is not None else None
+        mhz = sampler.summary().get("sm_mhz")
+        if wi and mhz and dom_ms > 0:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_i = 4 * sms * mhz * 1e6 / 1e9
+            issue = {"achieved": wi / (dom_ms * 1e-3) / 1e9, "peak": peak_i, "unit": "G warp instructions/s", "frac": wi / (dom_ms * 1e-3) / 1e9 / peak_i,
+                     "warp_instructions_per_launch": wi, "note": "peak = 4 schedulers x SMs x sampled SM clock, one instruction per cycle; IMAD / LOP3 / SHF / SEL occupy "
+                     "their pipe for 2 cycles each on this part and do not overlap each other (profiles/r1_ubench_pipes.txt: 0.53 per cycle for such "
+                     "a mix), plain adds and predicate logic take 1"}
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "issue_bound": issue, "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dom_ms,
                 "note": "the coder is sequential per stream and bound by integer instruction issue (~1.9 cycles per integer instruction per scheduler, profiles/r1_ubench_pipes.txt; DRAM < 4 %): "
