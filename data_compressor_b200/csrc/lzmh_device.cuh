@@ -339,41 +339,24 @@ static const uint32_t kLzOutRing = 1024;    // bytes of output kept in shared me
 static const uint32_t kLzOutFlush = 512;    // bytes per flush
 static const uint32_t kLzModTab = 32 * 32 + 32;   // [back][lane] = lane % back for back < 32, then [back] = 32 % back
 
-// The words a stream shares with its neighbours are read byte by byte, the stream's own bytes only (once or twice per
-// stream: kept out of line)
-__device__ __noinline__ uint32_t lz_load_edge(const uint32_t *p, const uint8_t *bfirst, const uint8_t *bend)
-{
-  const uint8_t *b = reinterpret_cast<const uint8_t *>(p);
-  uint32_t w = 0;
-  for (int k = 0; k < 4; k++)
-    if (b + k >= bfirst && b + k < bend)
-      w |= (uint32_t)__ldg(b + k) << (24 - 8 * k);
-  return w;
-}
-
 struct LzWarpBits   // warp-uniform MSB-first bit source
 {
   const uint32_t *pchunk;   // word 0 of the 32-word chunk the lanes hold in w0 (w1: the chunk after it)
   const uint32_t *plast;    // the word with the stream's last bit
-  const uint8_t *bend;      // the end of the stream's bytes
   uint32_t last_mask;       // its stream bits
   uint32_t w0, w1, lane;
   uint32_t wi;              // next word of the chunk to hand out
   uint32_t a_hi, a_lo;      // the next 64 bits of the stream, left-aligned, zero beyond its end
   uint32_t valid;           // how many of them are loaded: 33..64 between tokens
 
-  __device__ __forceinline__ uint32_t load_edge(const uint32_t *p, const uint8_t *bfirst) const
-  {
-    const uint32_t w = lz_load_edge(p, bfirst, bend);
-    return p == plast ? w & last_mask : w;
-  }
-  __device__ __forceinline__ uint32_t load(const uint32_t *p) const   // any word but the stream's first
+  // Whole aligned words, like BitReader: a word that holds a byte of the stream lies inside the allocation the stream
+  // lies in (device allocations are multiples of 256 bytes), so nothing outside the caller's buffer is touched.
+  __device__ __forceinline__ uint32_t load(const uint32_t *p) const
   {
     if (p > plast)
       return 0u;
-    if (p == plast)
-      return load_edge(p, reinterpret_cast<const uint8_t *>(p));
-    return __byte_perm(__ldg(p), 0, 0x0123);
+    const uint32_t w = __byte_perm(__ldg(p), 0, 0x0123);
+    return p == plast ? w & last_mask : w;
   }
   __device__ __forceinline__ uint32_t next_word()
   {
@@ -406,11 +389,10 @@ struct LzWarpBits   // warp-uniform MSB-first bit source
     const uint32_t *base = reinterpret_cast<const uint32_t *>(p - mis);
     const uint64_t end = mis * 8 + nbits;
     plast = nbits ? base + ((end - 1) >> 5) : base - 1;
-    bend = p + ((nbits + 7) >> 3);
     last_mask = 0xFFFFFFFFu << (31 - ((uint32_t)(end - 1) & 31));
     lane = lane_;
     pchunk = base;
-    w0 = lane == 0 ? (base > plast ? 0u : load_edge(base, p)) : load(base + lane);
+    w0 = load(base + lane);
     w1 = load(base + 32 + lane);
     wi = 0;
     a_hi = next_word();
