@@ -601,6 +601,82 @@ def run_sweep(args):
                 del y
 
 
+# --------------------------------------------------------------------------------------------------------------
+# the csv codec through the host-buffer calls (text in pinned host memory, copies inside the timed region);
+# the reference's ReadCSV / WriteCSV (one loop each: one host core) timed on a bounded sample of the same text.
+def _csv_ref_worker(arg):
+    kind, text = arg
+    from oracle import binding as ob
+    impl = ob.Ref() if kind == "reference" else ob.Oracle()
+    t0 = time.perf_counter()
+    v = impl.csv_decode(text)
+    t1 = time.perf_counter()
+    back = impl.csv_encode(v)
+    t2 = time.perf_counter()
+    return v.size, t1 - t0, t2 - t1, back == text
+
+
+def run_csv(args):
+    import ctypes as C
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from data_compressor_b200 import Context, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: data_compressor_b200 has no CPU fallback")
+    ctx = Context(0)
+    n_ch = max(1, args.csv_lines // SAMPLES)
+    x = synth.redd_like(n_ch, SAMPLES, device="cuda").cpu().numpy().reshape(-1)     # two-decimal watt readings, like DCCLI/testdata/input.txt
+    text = ctx.csv_encode(x)                                                         # the text itself comes from the library (checked below)
+    n_lines = x.size
+    pin_t = torch.empty(len(text), dtype=torch.uint8).pin_memory()
+    pin_t.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
+    pin_v = torch.empty(n_lines, dtype=torch.float32).pin_memory()
+    pin_o = torch.empty(len(text) + 64, dtype=torch.uint8).pin_memory()
+    n, m = C.c_uint64(0), C.c_uint64(0)
+    steps, warm = max(1, min(args.steps, 10)), 3
+    t_dec = t_enc = 0.0
+    launches0 = ctx.launch_count()
+    gc.collect()
+    gc.disable()
+    for it in range(warm + steps):
+        t0 = time.perf_counter()
+        rc = ctx.lib.dc_csv_decode_host(ctx.h, pin_t.data_ptr(), len(text), 1, b",", pin_v.data_ptr(), n_lines, C.byref(n))
+        t1 = time.perf_counter()
+        rc2 = ctx.lib.dc_csv_encode_host(ctx.h, pin_v.data_ptr(), n_lines, 1, b",", 2, pin_o.data_ptr(), pin_o.numel(), C.byref(m))
+        t2 = time.perf_counter()
+        assert rc == 0 and rc2 == 0 and n.value == n_lines and m.value == len(text)
+        if it >= warm:
+            t_dec += t1 - t0
+            t_enc += t2 - t1
+    gc.enable()
+    launches = (ctx.launch_count() - launches0) // (warm + steps) * steps
+    ok = bool(np.array_equal(pin_v.numpy().view(np.uint32), x.view(np.uint32))) and pin_o.numpy()[: len(text)].tobytes() == text
+    dec_s, enc_s = t_dec / steps, t_enc / steps
+    cpu = None
+    if not args.no_cpu:
+        from oracle import binding as ob
+        ob.build(ref=os.path.isdir("/root/reference/DataCompressor"))
+        kind = cpu_kind()
+        sample_lines = min(n_lines, int(args.cpu_seconds * 1.0e6))                   # ~2 M lines/s each way on one core
+        cut = text.rfind(b"\n", 0, min(len(text), sample_lines * 6)) + 1            # ~6 bytes per line
+        with mp.get_context("spawn").Pool(1) as pool:
+            lines, ds, es, same = pool.map(_csv_ref_worker, [(kind, text[:cut])])[0]
+        cpu = {"value": lines / ds / 1e6, "unit": "M lines/s", "cores": 1, "kind": kind, "encode_value": lines / es / 1e6, "round_trip_ok": same,
+               "sample": f"{lines} lines ({cut / 1e6:.1f} MB of text), decode csv then encode csv, one core (ReadCSV and WriteCSV are single loops)"}
+    peak, peak_src = measured_peak()
+    alg = len(text) + 4 * n_lines
+    print(json.dumps({
+        "metric": "csv decode M lines/s through the host-buffer call", "value": n_lines / dec_s / 1e6, "unit": "M lines/s", "n_gpus": 1, "steps": steps,
+        "warmup": warm, "ms_per_step": dec_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->f32", "data": "synthetic",
+        "config": {"workload": f"SURVEY 8f-3: {n_lines} lines of two-decimal watt readings ({len(text) / 1e6:.1f} MB of text), column 1, pinned host buffers"},
+        "encode_value": n_lines / enc_s / 1e6, "encode_ms": enc_s * 1e3, "text_gbs": len(text) / dec_s / 1e9, "round_trip_ok": ok,
+        "e2e": {"value": n_lines / dec_s / 1e6, "unit": "M lines/s", "h2d_bytes_per_step": len(text), "d2h_bytes_per_step": 4 * n_lines},
+        "roofline": {"bound": "pcie", "achieved": alg / dec_s / 1e9, "unit": "GB/s", "peak": None, "frac": None, "traffic": None,
+                     "note": "the call is two PCIe copies (text in, floats out) around ~1.5 ms of kernels: profiles/r1_csv_codec.txt"},
+        "cpu_baseline": cpu, "gpu_launches": launches}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -614,7 +690,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="dega", choices=["dega", "axdr", "lzmh", "sweep"], help="dega = the contract line; axdr/lzmh = secondary paths; sweep = configs[4]")
+    ap.add_argument("--workload", default="dega", choices=["dega", "axdr", "lzmh", "sweep", "csv"],
+                    help="dega = the contract line; axdr/lzmh = secondary paths; sweep = configs[4]; csv = the text codec (SURVEY 8f-3)")
+    ap.add_argument("--csv-lines", type=int, default=50_000_000)
     ap.add_argument("--meters", type=int, default=1_000_000)
     ap.add_argument("--valuesize", type=int, default=32)
     ap.add_argument("--blocks", type=int, default=16384)
@@ -623,6 +701,8 @@ def main():
         run_reference(args)
     elif args.workload == "sweep":
         run_sweep(args)
+    elif args.workload == "csv":
+        run_csv(args)
     elif args.workload != "dega":
         run_secondary(args)
     else:
