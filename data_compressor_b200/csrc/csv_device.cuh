@@ -1,4 +1,5 @@
-// csv_device.cuh -- per-value body of `encode csv` (DCLib/src/csv.c:46-65, WriteCSV): printf("%.*f\n") of a float32.
+// csv_device.cuh -- per-value bodies of the csv codec: `encode csv` (DCLib/src/csv.c:46-65, WriteCSV) = printf("%.*f\n") of
+// a float32, described next, and `decode csv`'s field conversion (csv_to_float, at the end).
 //
 // WriteCSV prints every value with sprintf("%.*f\n", num_decimal_places, value) (csv.c:59).  printf converts the exact
 // binary value and rounds it to the requested digits half-to-even; the sign bit prints as '-' (also for zero and nan),
@@ -168,6 +169,112 @@ __host__ __device__ __forceinline__ uint32_t csv_print(const uint32_t bits, cons
     *q = '\n';
   }
   return len + nd + point + d + 1;
+}
+
+// ---- `decode csv`: one field -> float32 --------------------------------------------------------------------------
+__device__ __forceinline__ bool csv_is_space(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+__device__ __forceinline__ bool csv_is_digit(uint8_t c) { return c >= '0' && c <= '9'; }
+
+// strtof on text[fs, fe) for the part of its grammar that one correctly rounded operation converts (see the head of
+// csv_kernels.cu); `hard` is set for the rest (the returned value is then meaningless and the caller asks strtof).
+__device__ inline float csv_to_float(const uint8_t *text, const uint64_t fs, const uint64_t fe, bool &hard_out)
+{
+  const float pow10f[11] = { 1.0f, 10.0f, 100.0f, 1000.0f, 10000.0f, 100000.0f, 1000000.0f, 10000000.0f, 100000000.0f, 1000000000.0f, 10000000000.0f };
+  uint64_t i = fs;
+  while (i < fe && csv_is_space(text[i]))
+    i++;
+  bool neg = false;
+  if (i < fe && (text[i] == '+' || text[i] == '-'))
+    neg = text[i++] == '-';
+  const uint64_t num_start = i;
+  uint64_t M = 0;
+  uint32_t sig = 0, k = 0, ndig = 0;
+  bool hard = false, frac = false;
+  for (; i < fe; i++)
+  {
+    const uint8_t c = text[i];
+    if (csv_is_digit(c))
+    {
+      ndig++;
+      if (sig > 0 || c != '0')
+      {
+        if (sig < 19)
+          M = M * 10 + (uint64_t)(c - '0');
+        else
+          hard = true;
+        sig++;
+      }
+      if (frac)
+        k++;
+    }
+    else if (c == '.' && !frac)
+      frac = true;
+    else
+      break;
+  }
+  float f = 0.0f;
+  if (ndig == 0)
+  {
+    // no conversion: strtof returns +0 ... unless the text spells inf / nan
+    if (i < fe && (text[i] == 'i' || text[i] == 'I' || text[i] == 'n' || text[i] == 'N'))
+      hard = true;
+    neg = false;
+  }
+  else
+  {
+    const uint8_t c = i < fe ? text[i] : 0;
+    if ((c == 'x' || c == 'X') && i == num_start + 1 && text[num_start] == '0')
+      hard = true;                                            // hex float
+    // decimal exponent: e[+-]digits; an 'e' without digits is not part of the number (strtof stops before it)
+    int e10 = 0;
+    if ((c == 'e' || c == 'E') && !hard)
+    {
+      uint64_t q = i + 1;
+      bool eneg = false;
+      if (q < fe && (text[q] == '+' || text[q] == '-'))
+        eneg = text[q++] == '-';
+      if (q < fe && csv_is_digit(text[q]))
+      {
+        uint32_t ev = 0;
+        for (; q < fe && csv_is_digit(text[q]); q++)
+          ev = ev < 100000u ? ev * 10 + (uint32_t)(text[q] - '0') : ev;
+        e10 = eneg ? -(int)ev : (int)ev;
+      }
+    }
+    while (M != 0 && M % 10 == 0 && sig > 1)                  // trailing zeros of the digit string move into the exponent
+    {
+      M /= 10;
+      e10++;
+      sig--;
+    }
+    e10 -= (int)k;                                            // value = M * 10^e10
+    if (hard)
+      ;
+    else if (M == 0)
+      f = 0.0f;
+    else if (e10 == 0)
+      f = __ull2float_rn(M);                                  // exact integer, one rounding
+    else if (e10 < 0)
+    {
+      if (M < (1ull << 24) && e10 >= -10)
+        f = __fdiv_rn((float)M, pow10f[-e10]);                // both operands exact: the division rounds once
+      else
+        hard = true;
+    }
+    else if (sig + (uint32_t)e10 <= 19)
+    {
+      uint64_t v = M;
+      for (int t = 0; t < e10; t++)
+        v *= 10;
+      f = __ull2float_rn(v);
+    }
+    else if (M < (1ull << 24) && e10 <= 10)
+      f = __fmul_rn((float)M, pow10f[e10]);
+    else
+      hard = true;
+  }
+  hard_out = hard;
+  return neg ? -f : f;
 }
 
 }  // namespace dc

@@ -13,9 +13,9 @@
 // [space]* [+-]? digits [. digits]  whose digits, after dropping leading zeros and trailing fraction zeros, make an
 // integer M < 2^24 with at most ten fraction digits k is converted as float(M) / 10^k: both operands are exact in
 // binary32, so the IEEE division is the correctly rounded result, i.e. strtof's.  Integers without a fraction up to
-// 19 digits go through the correctly rounded integer -> float conversion.  Everything else strtof accepts (exponents,
-// hex floats, inf/nan, more digits) is flagged and converted by the caller with strtof itself; meter readings never
-// get there.
+// 19 digits go through the correctly rounded integer -> float conversion; a decimal exponent shifts k (M * 10^e with e <= 10
+// is one correctly rounded multiplication).  What is left of strtof's grammar (hex floats, inf/nan, more digits, large
+// exponents) is flagged and converted by the caller with strtof itself; meter readings never get there.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -82,16 +82,12 @@ __global__ void __launch_bounds__(kCsvThreads) csv_lines_kernel(const uint8_t *t
   }
 }
 
-__device__ __forceinline__ bool csv_is_space(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
-__device__ __forceinline__ bool csv_is_digit(uint8_t c) { return c >= '0' && c <= '9'; }
-
 // value[j], flag8[j] (8 = the line has the column, 0 = it does not), and the indices of fields strtof has to convert
 __global__ void __launch_bounds__(256) csv_parse_kernel(const uint8_t *text, uint64_t n, const uint64_t *line_end, uint64_t n_newlines,
                                                         uint64_t n_lines, uint32_t column, uint8_t sep, float *value, uint64_t *flag8,
                                                         uint64_t *field_lo, uint64_t *field_hi, unsigned long long *n_hard,
                                                         uint64_t *hard_list, uint64_t hard_cap)
 {
-  const float pow10f[11] = { 1.0f, 10.0f, 100.0f, 1000.0f, 10000.0f, 100000.0f, 1000000.0f, 10000000.0f, 100000000.0f, 1000000000.0f, 10000000000.0f };
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_lines; j += (uint64_t)gridDim.x * blockDim.x)
   {
     const uint64_t start = j == 0 ? 0 : line_end[j - 1] + 1;
@@ -121,70 +117,8 @@ __global__ void __launch_bounds__(256) csv_parse_kernel(const uint8_t *text, uin
     field_hi[j] = fe;
     if (!have)
       continue;
-    // ---- strtof on text[fs, fe)
-    uint64_t i = fs;
-    while (i < fe && csv_is_space(text[i]))
-      i++;
-    bool neg = false;
-    if (i < fe && (text[i] == '+' || text[i] == '-'))
-      neg = text[i++] == '-';
-    const uint64_t num_start = i;
-    uint64_t M = 0;
-    uint32_t sig = 0, k = 0, ndig = 0;
-    bool hard = false, frac = false;
-    for (; i < fe; i++)
-    {
-      const uint8_t c = text[i];
-      if (csv_is_digit(c))
-      {
-        ndig++;
-        if (sig > 0 || c != '0')
-        {
-          if (sig < 19)
-            M = M * 10 + (uint64_t)(c - '0');
-          else
-            hard = true;
-          sig++;
-        }
-        if (frac)
-          k++;
-      }
-      else if (c == '.' && !frac)
-        frac = true;
-      else
-        break;
-    }
-    float f = 0.0f;
-    if (ndig == 0)
-    {
-      // no conversion: strtof returns +0 ... unless the text spells inf / nan
-      if (i < fe && (text[i] == 'i' || text[i] == 'I' || text[i] == 'n' || text[i] == 'N'))
-        hard = true;
-      neg = false;
-    }
-    else
-    {
-      const uint8_t c = i < fe ? text[i] : 0;
-      if (c == 'e' || c == 'E' || c == 'p' || c == 'P')
-        hard = true;                                            // possibly an exponent
-      if ((c == 'x' || c == 'X') && i == num_start + 1 && text[num_start] == '0')
-        hard = true;                                            // hex float
-      while (k > 0 && M != 0 && M % 10 == 0)                    // trailing fraction zeros carry no information
-      {
-        M /= 10;
-        k--;
-        sig--;
-      }
-      if (M == 0)
-        f = 0.0f;
-      else if (k == 0 && sig <= 19)
-        f = __ull2float_rn(M);
-      else if (M < (1ull << 24) && k <= 10)
-        f = __fdiv_rn((float)M, pow10f[k]);
-      else
-        hard = true;
-    }
-    value[j] = neg ? -f : f;
+    bool hard;
+    value[j] = csv_to_float(text, fs, fe, hard);   // strtof on text[fs, fe)
     if (hard)
     {
       const unsigned long long h = atomicAdd(n_hard, 1ull);

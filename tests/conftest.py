@@ -87,9 +87,18 @@ class Sim:
         L.sim_dega_decode_batch.restype = C.c_int
         L.sim_dega_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_csv_field.restype = C.c_float
+        L.sim_csv_field.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_int)]
         L.sim_csv_encode.restype = C.c_uint64
         L.sim_csv_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_uint64]
         self.lib = L
+
+    def csv_field(self, field: str):
+        """(value, hard) of csv_to_float on one field."""
+        b = field.encode()
+        hard = C.c_int(0)
+        v = self.lib.sim_csv_field(b, len(b), C.byref(hard))
+        return np.float32(v), bool(hard.value)
 
     def csv_encode(self, values, column=1, separator=",", decimals=2) -> bytes:
         x = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)

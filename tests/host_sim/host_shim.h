@@ -84,6 +84,7 @@ static inline long long __float2ll_rz(float v)
   return (long long)v;
 }
 static inline float __ll2float_rn(long long v) { return (float)v; }
+static inline float __ull2float_rn(unsigned long long v) { return (float)v; }
 static inline float __int2float_rn(int v) { return (float)v; }
 static inline unsigned int __float2uint_rz(float v)
 {

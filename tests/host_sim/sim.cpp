@@ -29,6 +29,15 @@ static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
+// `decode csv`'s conversion of one field (csv_to_float); *hard = 1 when the field is left to strtof
+float sim_csv_field(const uint8_t *text, uint64_t n, int *hard)
+{
+  bool h = false;
+  const float f = dc::csv_to_float(text, 0, n, h);
+  *hard = h ? 1 : 0;
+  return f;
+}
+
 // the two passes of `encode csv` (csv_measure_kernel / csv_write_kernel) over n values, sequentially; returns the text length
 uint64_t sim_csv_encode(const uint32_t *values, uint64_t n, uint32_t column, char sep, uint32_t decimals, uint8_t *text, uint64_t cap)
 {

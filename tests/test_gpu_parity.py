@@ -501,12 +501,30 @@ def test_csv_encode_matches_oracle(ctx, oracle, golden):
     assert ctx.csv_encode(big_n, 2, ",", 3) == oracle.csv_encode(big_n, 2, ",", 3)
 
 
+def test_csv_decode_exponent_forms(ctx, oracle):
+    """Decimal exponents are converted on the device when one correctly rounded operation does it; everything is compared
+    with strtof (the oracle), whichever route a field takes."""
+    rng = np.random.default_rng(9)
+    rows = []
+    for _ in range(20000):
+        m = int(rng.integers(0, 10 ** int(rng.integers(1, 12))))
+        frac = int(rng.integers(0, 8))
+        e = int(rng.integers(-14, 15))
+        body = f"{m / 10 ** frac:.{frac}f}" if rng.random() < 0.7 else str(m)
+        rows.append(f"{'-' if rng.random() < 0.3 else ''}{body}{'eE'[int(rng.integers(0, 2))]}{'+' if e >= 0 and rng.random() < 0.5 else ''}{e}")
+    rows += ["1e", "1e+", "1e-", "1.5e", "2E+x", "1e5x", "1p3", "12e00", "12e-00", "0e5", "0.0e-3", "1000e-3", "1e10", "1e11", "123456789e11",
+             "1e38", "1e39", "1e-38", "1e-46", "9999999999999999999e0", "99999999999999999999e0", "16777217e0", "1.6777217e7", "1e99999999999"]
+    text = "\n".join(rows) + "\n"
+    got, want = ctx.csv_decode(text), oracle.csv_decode(text)
+    assert got.size == len(rows) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_csv_decode_many_strtof_fields(ctx, oracle):
     """More fields outside the fast grammar than the first pass keeps track of (65 536): the parse phase reruns with the
     exact list size and every one of them still gets strtof's value."""
     rng = np.random.default_rng(5)
     vals = rng.integers(1, 10 ** 6, 150000)
-    text = "".join(f"{v}e-2\n" if i % 2 else f"{v / 100:.2f}\n" for i, v in enumerate(vals))
+    text = "".join(f"0x{v:x}p-2\n" if i % 2 else f"{v / 100:.2f}\n" for i, v in enumerate(vals))      # hex floats: strtof's business
     got, want = ctx.csv_decode(text), oracle.csv_decode(text)
     assert got.size == vals.size and np.array_equal(got.view(np.uint32), want.view(np.uint32))
 

@@ -182,3 +182,32 @@ def test_csv_print_matches_oracle(sim, oracle):
     for d in range(7):
         for col, sep in ((1, ","), (4, ";")):
             assert sim.csv_encode(x, col, sep, d) == oracle.csv_encode(x, col, sep, d), (d, col)
+
+
+def test_csv_field_conversion_matches_strtof(sim, oracle):
+    """csv_to_float (csv_device.cuh) against strtof for every field it does not hand over, and the hand-over itself for
+    the forms that need it."""
+    rng = np.random.default_rng(31)
+    fields = ["0", "-0", "+0.0", "1", "1.5", "-2.25", " 7", "\t8.5", "00012.50", "-000.0100", "5.", ".5", "-.5", ".", "-", "", "abc", "1.2.3", "--4", "+-4",
+              "9.75x", "123456789", "1234567890123456789", "12345678901234567890", "0.000012345", "1234.500000", "16777216", "16777217", "16777219",
+              "0.1", "0.12345678", "0.1234567891", "99999999", "3.4028235e38", "3.4028236e38", "1e", "1e+", "1e-", "1.5e", "2E+x", "1e5x", "1p3", "12e00",
+              "12e-00", "0e5", "0.0e-3", "1000e-3", "1e10", "1e11", "123456789e11", "1e38", "1e39", "1e-38", "1e-46", "9999999999999999999e0",
+              "16777217e0", "1.6777217e7", "1e99999999999", "-2.5E-3", "0x10", "0x1p4", "0x", "0xg", "inf", "-inf", "INFINITY", "nan", "NaN(12)", "1e-10", "1e-11"]
+    for _ in range(30000):
+        s = str(int("".join(str(d) for d in rng.integers(0, 10, int(rng.integers(1, 21))))))      # up to 20 digits
+        frac = int(rng.integers(0, 12))
+        body = (s[:-frac] or "0") + "." + s[-frac:].rjust(frac, "0") if frac else s
+        if rng.random() < 0.4:
+            body += "eE"[int(rng.integers(0, 2))] + ("+" if rng.random() < 0.3 else "") + str(int(rng.integers(-14, 15)))
+        fields.append(("-" if rng.random() < 0.3 else "") + body)
+    n_fast = 0
+    for f in fields:
+        v, hard = sim.csv_field(f)
+        want = oracle.csv_decode(f + "\n")
+        assert want.size == 1
+        if not hard:
+            n_fast += 1
+            assert v.view(np.uint32) == want.view(np.uint32)[0], (f, v, want[0])
+    assert all(sim.csv_field(f)[1] for f in ("0x10", "inf", "nan", "12345678901234567890", "1e39", "1e-46", "0.1234567891"))
+    assert not any(sim.csv_field(f)[1] for f in ("1.5", "123456789", "1e3", "-2.5E-3", "1e", "1p3", "", "abc", "1000e-3"))
+    assert n_fast > 5000

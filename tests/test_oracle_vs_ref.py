@@ -99,6 +99,7 @@ CSV_CASES = [
     "-0\n+3.25\n 7\n1e3\n0x10\ninf\nnan\n-.5\n5.\n.\n-\n123456789\n0.000012345\n1234.500000\n16777217\n3.4028236e38\n",
     "  \t9.75x\n1.2.3\n--4\n+-4\n1e\n1e+\n0x\n0xg\nINFINITY\nNaN(12)\n00012.50\n-000.0100\n99999999999999999999\n0.1234567891\n",
     "3;4;5\n6;7\n", "7\n8",
+    "1e\n1e+\n1.5e\n2E+x\n1p3\n12e00\n0e5\n1000e-3\n1e10\n1e11\n123456789e11\n1e38\n1e39\n1e-38\n1e-46\n16777217e0\n1.6777217e7\n-2.5E-3\n",
 ]
 
 
