@@ -176,9 +176,9 @@ int dc_aggregate_device(dc_ctx *ctx, const float *d_samples, uint64_t n_channels
 /* `decode csv [column=..] [separator=..]` (DCLib/src/csv.c:13-44, ReadCSV): the `column`-th field (counted
    from 1) of every line of `text` through strtof, in line order; lines without that field produce nothing,
    an unterminated last line counts.  Host buffers; line splitting, field search and the decimal -> float32
-   conversion run on the GPU (correctly rounded, i.e. strtof's result, for plain decimals of up to 7 significant
-   digits and integers of up to 19; anything else strtof accepts -- exponents, hex, inf/nan, longer digit
-   strings -- is converted by strtof on the host).  On DC_ERR_MEMORY *n_out holds the count needed. */
+   conversion run on the GPU (correctly rounded, i.e. strtof's result, for decimals of up to 7 significant digits,
+   with or without a small decimal exponent, and integers of up to 19 digits; what is left of strtof's grammar --
+   hex floats, inf/nan, longer digit strings, large exponents -- is converted by strtof on the host).  On DC_ERR_MEMORY *n_out holds the count needed. */
 int dc_csv_decode_host(dc_ctx *ctx, const uint8_t *text, uint64_t nbytes, uint32_t column, char separator,
                        float *out, uint64_t out_cap, uint64_t *n_out);
 
