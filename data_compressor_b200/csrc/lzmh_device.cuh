@@ -69,7 +69,7 @@ __device__ __forceinline__ void lz_token(int k, int off, int len, uint32_t &code
 #ifndef DC_HOST_SIM
 // ---------------------------------------------------------------------------------------------------------
 // Encoder, one warp per stream.  `win` is this warp's shared-memory window, `lsym`/`lcnt` its rank list.
-static const int kLzWin = 1024;   // bytes of the stream kept in shared memory per warp
+static const int kLzWin = 2048;   // bytes of the stream kept in shared memory per warp (1024: 3.6 % slower, 4096: no better)
 static const int kLzWinPad = 16;  // readable slack behind the window (word-wise match compare)
 
 // shared memory through 32-bit addresses (the generic-pointer form recomputes the window base in the token loop)
