@@ -447,6 +447,7 @@ __device__ inline void lzmh_decode_warp(const LzmhArgs &a, const uint64_t s, con
           out[flushed + i] = (uint8_t)lds_u8(ring + ((slot + i) & (kLzOutRing - 1)));
     flushed += n;
     pend -= n;
+    __syncwarp();   // the ring slots just read may be written again by the next token (pend can exceed 750 of the 1024)
   };
 
   for (;;)
