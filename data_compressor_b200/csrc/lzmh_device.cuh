@@ -333,8 +333,9 @@ __device__ inline void lzmh_encode_warp(const LzmhArgs &a, const uint64_t s, uin
 // stops when the input is used up and the window is empty (lzmh.c:571).  Here the window is the top of a 64-bit
 // accumulator of the stream with zeros behind its last bit, and `rem` counts the bits no token has used yet:
 // have = min(25, rem), "input used up" = rem <= 25 when the token started, "window empty" = accumulator zero.
-// About 45 warp instructions per token; the first version (separate window, 64-bit positions, a division per
-// overlapping copy) took 150.
+// 83 warp instructions per token; the first version (separate window, 64-bit positions, a division per overlapping
+// copy) took 150.  Tried and measured no better: the rank list in registers (two packed entries per lane, shuffles instead of
+// shared memory: 12.9 ms against 12.65), byte-wise loads at the stream edges (one CTA per SM less: 13.0 ms).
 static const uint32_t kLzOutRing = 1024;    // bytes of output kept in shared memory per warp (power of two)
 static const uint32_t kLzOutFlush = 512;    // bytes per flush
 static const uint32_t kLzModTab = 32 * 32 + 32;   // [back][lane] = lane % back for back < 32, then [back] = 32 % back
