@@ -102,9 +102,9 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
     back_body(a, s);
 }
 
-// measured 1.32 ms at 10 CTAs per SM, 1.38 at 8, 1.36 at 12, 1.46 at 16
+// measured (final kernel): 1.235 ms at 12 CTAs per SM, 1.245 at 11, 1.255 at 10, 1.29 at 8, 1.39+ at 13 and more (32 registers: spills)
 #ifndef BACK_MIN_CTAS
-#define BACK_MIN_CTAS 10
+#define BACK_MIN_CTAS 12
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, BACK_MIN_CTAS) back_dega_kernel(const BackArgs a)
