@@ -1,7 +1,7 @@
 /* ref_driver.c -- in-process driver for the UNMODIFIED reference codecs (test infrastructure only).
  *
  * Linked by oracle/Makefile against objects compiled directly from
- * /root/reference/DataCompressor/{DCIOLib,DCLib}/src/*.c (release flags of
+ * /root/reference/DataCompressor/{DCIOLib,DCLib}/src, every .c file (release flags of
  * common/build/gcc/common.mak:11-20) into oracle/_ref/libdcref.so.  It replays what DCCLI's stage
  * loop does (DCCLI/src/cli.c:430-466): every stage runs to completion on in-memory bit buffers and
  * the write->read mode switch keeps the fractional last byte (cli.c:212-223), so stage N+1 sees the
