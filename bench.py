@@ -5,10 +5,13 @@
     python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path on the host cores
 
 Workload = BASELINE.json configs[1]: synthetic REDD-like 1 Hz load profiles, 4096 channels x 1 day per GPU,
-DEGA (normalize -> diff -> seg -> bac adaptive) encode + decode, channels cut into resumable 1024-sample blocks.
+DEGA (normalize -> diff -> seg -> bac adaptive) encode + decode, channels cut into resumable blocks.  The block
+length is derived from the device (Context.two_wave_block_len: the shortest block whose stream count fits two waves
+of the coder kernels, 1168 samples on a 148-SM B200); the line also carries the same step at 1024-sample blocks and
+with whole channels (the reference's own unit of work), so the fitted figure is not the only one.
 A "step" is one encode + one decode of every stream on the rank.  `value` counts the raw float32 bytes once per
 step (GB/s of raw samples through the encode+decode round trip), inputs resident in HBM; `e2e` is the same
-step through the host-buffer C ABI (dc_dega_encode_host / dc_dega_decode_host) with pinned host memory.
+step through the host-buffer C ABI (dc_dega_encode_host[_async] / dc_dega_decode_host[_async]) with pinned host memory.
 """
 from __future__ import annotations
 
@@ -28,7 +31,8 @@ if ROOT not in sys.path:
 
 CHANNELS = 4096
 SAMPLES = 86400
-BLOCK_LEN = 1168   # 74 blocks per channel-day -> 303104 streams = exactly 2 waves of 148 SMs x 1024 threads
+BLOCK_LEN = 1168   # what Context.two_wave_block_len gives on a 148-SM B200 (74 blocks per channel-day -> 303104 streams = 2 waves of
+                   # 148 SMs x 1024 threads); only used where no GPU context exists to ask (the --impl reference arm off a GPU box)
 VS, NF, ADAPTIVE = 32, 100.0, True
 METRIC = "DEGA encode+decode GB/s of raw samples"
 
@@ -200,10 +204,28 @@ def cpu_sample(n_blocks, block_len, seed=0xDC0000):
 
 
 # --------------------------------------------------------------------------------------------------------------
+def resolve_block_len(args, ctx=None):
+    """--block-len -1 (default) = the two-wave block length of the device in use."""
+    if args.block_len >= 0:
+        return args.block_len
+    try:
+        if ctx is None:
+            import torch
+            if torch.cuda.is_available():
+                from data_compressor_b200 import Context
+                ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+        if ctx is not None:
+            return ctx.two_wave_block_len(args.channels, args.samples)
+    except Exception:
+        pass
+    return BLOCK_LEN
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    args.block_len = resolve_block_len(args)   # same streams as our arm cuts on this box
     from oracle import binding
     binding.build(ref=os.path.isdir("/root/reference/DataCompressor"))
     kind = cpu_kind()
@@ -251,6 +273,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = Context(local)
+    args.block_len = resolve_block_len(args, ctx)
     C_, S_, L_ = args.channels, args.samples, args.block_len
     # shard = this rank's channels (weak scaling: every GPU gets its own 4096 channels, disjoint seeds)
     x = synth.redd_like(C_, S_, device=dev, seed=0xDC0000 + rank * C_)
@@ -263,9 +286,12 @@ def run_ours(args):
 
     def step():
         e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
-        # the only collective on the path: per-shard payload byte counts -> container offsets (8 B per rank)
-        shard.exchange_sizes(e.total_bytes, e.n_streams, dev)
+        # the only collective on the path: per-shard payload byte counts -> container offsets (16 B per rank).  It is
+        # started here and resolved after the decode: nothing in the decode needs the other ranks' sizes
+        pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
         ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+        if pending is not None:
+            pending.result()
         return e
 
     def barrier():
@@ -304,10 +330,11 @@ def run_ours(args):
         for it in range(args.steps):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
-            if world > 1:
-                shard.exchange_sizes(e.total_bytes, e.n_streams, dev)
+            pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
             ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
             km2 = ctx.kernel_ms()
+            if pending is not None:
+                sizes = pending.result()   # container offsets of this rank: inside the timed step, off its critical path
             for k, v in list(km.items()) + list(km2.items()):
                 kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             step_ev[it + 1].record(ctx.stream)
@@ -331,6 +358,40 @@ def run_ours(args):
     value = world * raw_bytes / (ms_per_step * 1e-3) / 1e9
     kernel_ms = {k: v / args.steps for k, v in kernel_ms.items()}
 
+    # ---- the same step at two other block lengths (not the contract value; kept beside it so that the fitted block
+    # length is not the only figure): 1024-sample blocks, and whole channels = the reference's own unit of work
+    other = {}
+    if not args.no_extra:
+        ctx.set_profiling(False)
+        for name, bl in (("block_len_1024", 1024), ("whole_channel", 0)):
+            if bl == L_:
+                continue
+            e2 = ctx.dega_encode(x, block_len=bl, vs=VS, nf=NF, adaptive=ADAPTIVE)
+            n_rep = 2 if bl == 0 else 5
+            for _ in range(2):
+                ctx.dega_decode(ctx.dega_encode(x, block_len=bl, vs=VS, nf=NF, adaptive=ADAPTIVE, out=e2), vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+            ta, tb, tc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            barrier()
+            with torch.cuda.stream(ctx.stream):
+                ta.record(ctx.stream)
+                for _ in range(n_rep):
+                    ctx.dega_encode(x, block_len=bl, vs=VS, nf=NF, adaptive=ADAPTIVE, out=e2)
+                tb.record(ctx.stream)
+                for _ in range(n_rep):
+                    ctx.dega_decode(e2, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+                tc.record(ctx.stream)
+            barrier()
+            enc_ms2, dec_ms2 = ta.elapsed_time(tb) / n_rep, tb.elapsed_time(tc) / n_rep
+            tt = torch.tensor([enc_ms2, dec_ms2], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            enc_ms2, dec_ms2 = float(tt[0].item()), float(tt[1].item())
+            ok = ok and bool(torch.equal(y.view(torch.int32), x.view(torch.int32)))
+            other[name] = {"block_len": bl, "streams_per_gpu": e2.n_streams, "encode_ms": enc_ms2, "decode_ms": dec_ms2,
+                           "value": world * raw_bytes / ((enc_ms2 + dec_ms2) * 1e-3) / 1e9, "encode_gbs": world * raw_bytes / (enc_ms2 * 1e-3) / 1e9,
+                           "decode_gbs": world * raw_bytes / (dec_ms2 * 1e-3) / 1e9, "compression_ratio": raw_bytes / e2.total_bytes}
+            del e2
+
     # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -339,29 +400,86 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         hxn = hx.numpy()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        kw = dict(vs=VS, nf=NF, adaptive=ADAPTIVE)
+        ekw = dict(kw, block_len=L_, payload_cap=int(enc.total_bytes * 1.05) + 4096)   # the compressed size is known from the device run
+        ctx2 = Context(local)   # the decoder's context: own streams and staging, so that its copies run beside the encoder's
         for _ in range(2):   # warm-up: the first calls page-lock ~3.3 GB of host buffers and size the device staging
-            pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
-            yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
+            for slot in (0, 1):
+                pay, bl, bo, st = ctx.dega_encode_host(hxn, slot=slot, **ekw)
+            yy2, n_out, st2 = ctx2.dega_decode_host(pay, bl, bo, C_, S_, L_, **kw)
+        # (a) one context, encode then decode: each call keeps one direction of the link busy
         barrier()
         gc.collect()
         gc.disable()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            pay, bl, bo, st = ctx.dega_encode_host(hxn, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
-            yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, vs=VS, nf=NF, adaptive=ADAPTIVE)
+            pay, bl, bo, st = ctx.dega_encode_host(hxn, slot=0, **ekw)
+            yy, n_out, st2 = ctx.dega_decode_host(pay, bl, bo, C_, S_, L_, **kw)
+        barrier()
+        dt_serial = (time.perf_counter() - t0) / e2e_steps
+        ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all())
+        # (b) two contexts: step i encodes the batch (host -> device heavy) while the payload step i-1 produced is
+        # decoded (device -> host heavy); every step still copies every input in and every result out
+        prev = ctx.dega_encode_host(hxn, slot=0, **ekw)
+        yy2.fill(0)   # the second context's output buffer: the check below must see what the timed steps wrote
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            pe = ctx.dega_encode_host(hxn, slot=(i + 1) % 2, wait=False, **ekw)
+            pd = ctx2.dega_decode_host(prev[0], prev[1], prev[2], C_, S_, L_, wait=False, **kw)
+            prev = pe.wait()
+            yy, n_out, st2 = pd.wait()
         barrier()
         dt = (time.perf_counter() - t0) / e2e_steps
         gc.enable()
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all()) and not bool(st2.any()) and not bool(prev[3].any())
+        pay = prev[0]
+        # (c) what the link itself allows for the same byte counts: pinned copies only, both directions at once
+        n_in = raw_bytes + pay.size
+        dbuf = torch.empty(n_in, dtype=torch.uint8, device=dev)
+        dbuf2 = torch.empty(n_in, dtype=torch.uint8, device=dev)
+        # the page-locked buffers the calls above used (no new pinned memory): samples + a payload in, samples + a payload out
+        hin = (hx.view(torch.uint8).reshape(-1), ctx._pinned_cache["enc_payload0"][: pay.size])
+        hout = (ctx2._pinned_cache["dec_samples"][: raw_bytes], ctx._pinned_cache["enc_payload1"][: pay.size])
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def copies(duplex):
+            barrier()
+            t = time.perf_counter()
+            for _ in range(2):
+                with torch.cuda.stream(s1):
+                    dbuf[: raw_bytes].copy_(hin[0], non_blocking=True)
+                    dbuf[raw_bytes:].copy_(hin[1], non_blocking=True)
+                if not duplex:
+                    s1.synchronize()
+                with torch.cuda.stream(s2):
+                    hout[0].copy_(dbuf2[: raw_bytes], non_blocking=True)
+                    hout[1].copy_(dbuf2[raw_bytes:], non_blocking=True)
+                s1.synchronize()
+                s2.synchronize()
+            barrier()
+            return (time.perf_counter() - t) / 2
+
+        copies(True)
+        floor_duplex, floor_serial = copies(True), copies(False)
+        del dbuf, dbuf2, hin, hout
+        tt = torch.tensor([dt, dt_serial, floor_duplex, floor_serial], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all())
+        dt, dt_serial, floor_duplex, floor_serial = (float(v) for v in tt.tolist())
         meta = n_streams * (8 + 8 + 4) + 8
         e2e = {"value": world * raw_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(raw_bytes + pay.size + meta), "d2h_bytes_per_step": int(raw_bytes + pay.size + 2 * meta),
-               "api": "dc_dega_encode_host + dc_dega_decode_host (include/dc_cuda.h), host buffers, copies inside the timed region",
-               "host_cpus_bound": numa_cpus}
+               "api": "dc_dega_encode_host_async on one context + dc_dega_decode_host_async on a second one, dc_wait on both (include/dc_cuda.h); "
+                      "host buffers, every copy inside the timed region; step i encodes the batch while the payload of step i-1 is decoded, "
+                      "so one encode and one decode of every stream complete per step and both PCIe directions carry data at once",
+               "serial_value": world * raw_bytes / dt_serial / 1e9, "serial_ms_per_step": dt_serial * 1e3,
+               "serial_api": "dc_dega_encode_host then dc_dega_decode_host on one context (each call uses one direction of the link)",
+               "pcie_floor_ms": floor_duplex * 1e3, "pcie_floor_serial_ms": floor_serial * 1e3,
+               "pcie_floor_note": f"pinned cudaMemcpyAsync of the same byte counts ({n_in} B each way), no kernels, measured on every rank at once (max over ranks): "
+                                  "both directions together / one after the other",
+               "frac_of_pcie_floor": floor_duplex / dt, "host_cpus_bound": numa_cpus}
+        ctx2.close()
 
     if rank != 0:
         if world > 1:
@@ -425,6 +543,7 @@ def run_ours(args):
         "encode_ms": sum(kernel_ms.get(k, 0.0) for k in ("front", "bac_encode", "scan", "gather")),
         "decode_ms": sum(kernel_ms.get(k, 0.0) for k in ("bac_decode", "back")),
         "kernel_ms": kernel_ms, "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)], "slowest_step": step_ms.index(max(step_ms)), "round_trip_ok": ok,
+        "other_block_lengths": other,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
@@ -508,7 +627,7 @@ def run_secondary(args):
     else:   # lzmh
         n_blocks, block = args.blocks, 65536
         chans = (n_blocks * block + 2 * 86400 - 1) // (2 * 86400)
-        data = synth.watts_u16(chans, 86400, device=dev, seed=0xDC0000 + rank * chans).reshape(-1)[: n_blocks * block].contiguous()
+        data = synth.lzmh_blocks(n_blocks, block, device=dev, seed=0xDC0000 + rank * chans)
         t_enc = t_dec = 0.0
         for it in range(warm + steps):
             payload, bit_len, byte_off, status, total, in_off = ctx.lzmh_encode(data, block_bytes=block)
@@ -685,7 +804,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS)
     ap.add_argument("--samples", type=int, default=SAMPLES)
-    ap.add_argument("--block-len", type=int, default=BLOCK_LEN)
+    ap.add_argument("--block-len", type=int, default=-1, help="samples per resumable block; 0 = whole channels; -1 = the device's two-wave length")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 1024-sample-block and whole-channel figures")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU-baseline work per core")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

@@ -74,12 +74,16 @@ SYMBOLS = {
     "dc_synchronize": (_I, [_P]),
     "dc_stream": (_P, [_P]),
     "dc_launch_count": (_U64, [_P]),
+    "dc_coder_wave_streams": (_U64, [_P]),
     "dc_set_profiling": (_I, [_P, _I]),
     "dc_get_kernel_ms": (_I, [_P, C.POINTER(C.c_float)]),
     "dc_dega_encode_device": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
     "dc_dega_decode_device": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
     "dc_dega_encode_host": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
     "dc_dega_decode_host": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
+    "dc_dega_encode_host_async": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
+    "dc_dega_decode_host_async": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
+    "dc_wait": (_I, [_P]),
     "dc_axdr_encode_device": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
     "dc_axdr_decode_device": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
     "dc_lzmh_encode_device": (_I, [_P, _P, _P, _U64, _P, _U64, _P, _P, _P, _PU64]),

@@ -40,6 +40,18 @@ class Encoded:
         return bytes(self.payload[o:o + n].cpu().numpy().tobytes())
 
 
+class Pending:
+    """A *_host_async call in flight on a context; wait() joins it (dc_wait) and returns what the blocking call returns."""
+
+    def __init__(self, ctx, what, result, keep=()):
+        self.ctx, self.what, self.result, self.keep = ctx, what, result, keep   # keep: the buffers the worker reads
+
+    def wait(self):
+        self.ctx._check(self.ctx.lib.dc_wait(self.ctx.h), self.what)
+        self.keep = ()
+        return self.result()
+
+
 class Context:
     """One dc_ctx: one GPU, one CUDA stream, one scratch arena.  Not re-entrant (like the reference codecs)."""
 
@@ -74,6 +86,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.dc_launch_count(self.h))
+
+    def coder_wave_streams(self) -> int:
+        """Streams the coder kernels hold in flight at once on this GPU (dc_coder_wave_streams)."""
+        return int(self.lib.dc_coder_wave_streams(self.h))
+
+    def two_wave_block_len(self, n_channels: int, channel_len: int) -> int:
+        """Shortest block length whose stream count fits two waves of the coder kernels (whole channels if even those
+        do not fill them)."""
+        per_channel = max(1, 2 * self.coder_wave_streams() // max(1, n_channels))
+        return 0 if per_channel <= 1 else -(-channel_len // per_channel)
 
     def set_profiling(self, enable: bool):
         self._check(self.lib.dc_set_profiling(self.h, 1 if enable else 0), "dc_set_profiling")
@@ -262,30 +284,38 @@ class Context:
         return buf.numpy()[:nbytes]
 
     def dega_encode_host(self, samples: np.ndarray, block_len: int = 0, vs: int = 32, nf: float = 100.0,
-                         adaptive: bool = True, payload_cap: int | None = None):
+                         adaptive: bool = True, payload_cap: int | None = None, wait: bool = True, slot: int = 0):
         """Host-buffer face (dc_dega_encode_host).  Outputs live in reusable pinned buffers owned by the context:
-        they stay valid until the next *_host encode call."""
+        they stay valid until the next *_host encode call.
+
+        wait=False starts the call (dc_dega_encode_host_async) and returns a Pending whose wait() gives the same
+        tuple; until then neither `samples` nor the context may be touched.  An encode in flight on one context next
+        to a decode on another uses the PCIe link in both directions at once.  `slot` picks one of several sets of
+        output buffers, so that the result of one call can still be read (e.g. decoded) while the next call runs."""
         x = np.ascontiguousarray(samples, dtype=np.float32)
         assert x.ndim == 2
         n_channels, channel_len = x.shape
         n = self.n_streams(n_channels, channel_len, block_len)
         if payload_cap is None:
             payload_cap = x.size * 4 + n * 16 + 64
-        payload = self._pinned("enc_payload", payload_cap)
-        bit_len = self._pinned("enc_bit_len", n * 8).view(np.uint64)
-        byte_off = self._pinned("enc_byte_off", (n + 1) * 8).view(np.uint64)
-        status = self._pinned("enc_status", n * 4).view(np.int32)
+        payload = self._pinned(f"enc_payload{slot}", payload_cap)
+        bit_len = self._pinned(f"enc_bit_len{slot}", n * 8).view(np.uint64)
+        byte_off = self._pinned(f"enc_byte_off{slot}", (n + 1) * 8).view(np.uint64)
+        status = self._pinned(f"enc_status{slot}", n * 4).view(np.int32)
         total = C.c_uint64(0)
         lay = self._layout(n_channels, channel_len, block_len)
         par = self._params(vs, nf, adaptive)
-        rc = self.lib.dc_dega_encode_host(self.h, x.ctypes.data, C.byref(lay), C.byref(par), payload.ctypes.data,
-                                          payload_cap, bit_len.ctypes.data, byte_off.ctypes.data, status.ctypes.data,
-                                          C.byref(total))
+        fn = self.lib.dc_dega_encode_host if wait else self.lib.dc_dega_encode_host_async
+        rc = fn(self.h, x.ctypes.data, C.byref(lay), C.byref(par), payload.ctypes.data, payload_cap, bit_len.ctypes.data,
+                byte_off.ctypes.data, status.ctypes.data, C.byref(total))
         self._check(rc, "dc_dega_encode_host")
-        return payload[: total.value], bit_len, byte_off, status
+        result = lambda: (payload[: total.value], bit_len, byte_off, status)
+        return result() if wait else Pending(self, "dc_dega_encode_host_async", result, keep=(x, total))
 
     def dega_decode_host(self, payload: np.ndarray, bit_len: np.ndarray, byte_off: np.ndarray, n_channels: int,
-                         channel_len: int, block_len: int = 0, vs: int = 32, nf: float = 100.0, adaptive: bool = True):
+                         channel_len: int, block_len: int = 0, vs: int = 32, nf: float = 100.0, adaptive: bool = True,
+                         wait: bool = True):
+        """Host-buffer face (dc_dega_decode_host); wait=False: see dega_encode_host."""
         p = np.ascontiguousarray(payload, dtype=np.uint8)
         bl = np.ascontiguousarray(bit_len, dtype=np.uint64)
         bo = np.ascontiguousarray(byte_off, dtype=np.uint64)
@@ -295,10 +325,11 @@ class Context:
         status = self._pinned("dec_status", n * 4).view(np.int32)
         lay = self._layout(n_channels, channel_len, block_len)
         par = self._params(vs, nf, adaptive)
-        rc = self.lib.dc_dega_decode_host(self.h, p.ctypes.data, p.size, bl.ctypes.data, bo.ctypes.data, C.byref(lay),
-                                          C.byref(par), out.ctypes.data, n_out.ctypes.data, status.ctypes.data)
+        fn = self.lib.dc_dega_decode_host if wait else self.lib.dc_dega_decode_host_async
+        rc = fn(self.h, p.ctypes.data, p.size, bl.ctypes.data, bo.ctypes.data, C.byref(lay), C.byref(par), out.ctypes.data,
+                n_out.ctypes.data, status.ctypes.data)
         self._check(rc, "dc_dega_decode_host")
-        return out, n_out, status
+        return (out, n_out, status) if wait else Pending(self, "dc_dega_decode_host_async", lambda: (out, n_out, status), keep=(p, bl, bo))
 
     # ---- plugin face: one stage, one stream, host bytes -------------------------------------------
     def stage_run(self, stage: int, data, nbits: int | None = None, vs: int = 32, nf: float = 100.0,

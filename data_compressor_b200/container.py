@@ -131,6 +131,8 @@ def load_encoded(path: str, device="cuda"):
     h = read_header(path)
     bl = read_index(path, h)
     off = byte_offsets(bl)
+    if int(off[-1]) != int(h.payload_bytes):   # a truncated or corrupt index: the decoders would read past the payload
+        raise DcError(-3, f"container index covers {int(off[-1])} payload bytes, header says {int(h.payload_bytes)}")
     pay = read_payload(path, h)
     payload = torch.empty(pay.size + 16, dtype=torch.uint8, device=device)
     payload[: pay.size] = torch.from_numpy(pay).to(device)

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dc_cuda.h"
@@ -38,6 +39,8 @@ struct dc_ctx
   int profiling;
   cudaEvent_t ev[2 * DC_K_COUNT];
   uint32_t ev_mask;   // kernels timed during the last call
+  std::thread *worker;   // the *_host_async call in flight (at most one per context), joined by dc_wait
+  int worker_rc;
   char err[256];
 };
 
@@ -119,9 +122,6 @@ int stage_reserve(dc_ctx *c, uint64_t bytes)
   CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
   if (c->stage)
     cudaFree(c->stage);
-  for (int i = 0; i < 2; i++)
-    if (c->chain[i])
-      cudaFree(c->chain[i]);
   c->stage = nullptr;
   c->stage_size = 0;
   const uint64_t want = round_up(bytes, 1 << 20);
@@ -447,8 +447,8 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
 }
 
 // ---- decode pipeline: [bac] -> back end ------------------------------------------------------------------
-int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const uint64_t *d_bit_len, const uint64_t *d_byte_off,
-                    const Layout &L, uint64_t max_len, const dc_params *p, float *d_samples, uint64_t *d_n_out, int32_t *d_status)
+int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, uint64_t payload_bytes, const uint64_t *d_bit_len,
+                    const uint64_t *d_byte_off, const Layout &L, uint64_t max_len, const dc_params *p, float *d_samples, uint64_t *d_n_out, int32_t *d_status)
 {
   const uint64_t n = L.n_streams;
   const uint32_t vs = p->value_size_bits;
@@ -466,6 +466,7 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, const u
 
   CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
   CU_TRY(c, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint64_t), c->stream), DC_ERR_LIBRARY_CALL);
+  launch_validate_index(d_bit_len, d_byte_off, n, payload_bytes, d_status, c->stream);   // the index is the caller's: never trust it
 
   BackArgs ka;
   memset(&ka, 0, sizeof(ka));
@@ -591,6 +592,7 @@ void dc_destroy(dc_ctx *c)
 {
   if (!c)
     return;
+  dc_wait(c);
   cudaSetDevice(c->device);
   if (c->stream)
     cudaStreamSynchronize(c->stream);
@@ -598,6 +600,9 @@ void dc_destroy(dc_ctx *c)
     cudaFree(c->arena);
   if (c->stage)
     cudaFree(c->stage);
+  for (int i = 0; i < 2; i++)
+    if (c->chain[i])
+      cudaFree(c->chain[i]);
   if (c->d_div)
     cudaFree(c->d_div);
   if (c->d_work)
@@ -647,6 +652,13 @@ int dc_synchronize(dc_ctx *c)
 void *dc_stream(dc_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 uint64_t dc_launch_count(const dc_ctx *c) { return c ? launch_counter() - c->launches_base : 0; }
+
+uint64_t dc_coder_wave_streams(dc_ctx *c)
+{
+  if (!c || cudaSetDevice(c->device) != cudaSuccess)
+    return 0;
+  return (uint64_t)sm_count() * (uint64_t)bac_threads_per_sm();
+}
 
 int dc_set_profiling(dc_ctx *c, int enable)
 {
@@ -725,7 +737,7 @@ static int decode_device_common(dc_ctx *c, FrontKind kind, const uint8_t *d_payl
     if (frc != DC_ERR_INVALID_MODE)
       return frc;
   }
-  return decode_pipeline(c, kind, d_payload, d_bit_len, d_byte_off, L, max_len, params, d_samples, d_n_out, d_status);
+  return decode_pipeline(c, kind, d_payload, payload_bytes, d_bit_len, d_byte_off, L, max_len, params, d_samples, d_n_out, d_status);
 }
 
 int dc_dega_encode_device(dc_ctx *c, const float *d_samples, const dc_layout *layout, const dc_params *params, uint8_t *d_payload,
@@ -925,7 +937,7 @@ static int host_chunks(const Layout &L, uint64_t n_channels)
 {
   if (L.sample_off != nullptr || n_channels < 2)
     return 1;
-  uint64_t per = 148ull * 256;   // streams per chunk: a quarter wave
+  uint64_t per = (uint64_t)sm_count() * 256;   // streams per chunk: a quarter wave of the coder kernels (1024 threads per SM)
   if (const char *e = getenv("DC_HOST_CHUNK_STREAMS"))
     per = strtoull(e, nullptr, 10) > 0 ? strtoull(e, nullptr, 10) : per;
   uint64_t k = L.n_streams / per;
@@ -958,13 +970,15 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
   if (rc != DC_OK)
     return rc;
   const uint64_t n = L.n_streams;
-  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_cap, 4) + 256, 1) + Bump::size_of(n, 8) +
+  // device payload: every chunk starts 16-byte aligned, so up to 15 bytes of padding per chunk on top of the capacity
+  const uint64_t dev_payload_cap = round_up(payload_cap, 16) + 16ull * kMaxHostChunks + 256;
+  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(dev_payload_cap, 1) + Bump::size_of(n, 8) +
                         2 * Bump::size_of(n + 8, 8) + Bump::size_of(n, 4) + 4096;
   if ((rc = stage_reserve(c, need)) != DC_OK)
     return rc;
   Bump b(c->stage);
   float *d_samples = b.take<float>(total);
-  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_cap, 4) + 256);
+  uint8_t *d_payload = b.take<uint8_t>(dev_payload_cap);
   uint64_t *d_bits = b.take<uint64_t>(n);
   uint64_t *d_boff = b.take<uint64_t>(n + 8);
   uint64_t *d_off = b.take<uint64_t>(n + 8);
@@ -1000,7 +1014,9 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
     CU_TRY(c, cudaEventRecord(c->ev_in[k], c->s_h2d), DC_ERR_LIBRARY_CALL);
     return DC_OK;
   };
-  uint64_t base = 0;   // payload bytes of the chunks before this one
+  uint64_t base = 0;       // payload bytes of the chunks before this one (host side: packed densely)
+  uint64_t dev_base = 0;   // where this chunk's payload starts on the device: 16-byte aligned and past everything the chunks
+                           // before it wrote there (their copies to the host may still be in flight on s_d2h)
   uint64_t chunk_base[kMaxHostChunks], chunk_first[kMaxHostChunks], chunk_count[kMaxHostChunks];
   int result = DC_OK;
   if ((rc = upload(0)) != DC_OK)
@@ -1018,8 +1034,6 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
     CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
     uint64_t tot = 0;
     const uint64_t cap_left = payload_cap > base ? payload_cap - base : 0;
-    // chunk payloads start 16-byte aligned on the device; the host copy below packs them densely
-    const uint64_t dev_base = round_up(base, 16);
     rc = encode_pipeline(c, FRONT_DEGA, d_samples + (n_chunks == 1 ? 0 : c0 * L.channel_len), Lk, max_len, params, d_payload + dev_base,
                          cap_left, d_bits + s0, d_boff + s0, d_status + s0, &tot);
     if (rc != DC_OK && rc != DC_ERR_MEMORY)
@@ -1040,6 +1054,7 @@ int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout
     chunk_first[k] = s0;
     chunk_count[k] = nk;
     base += tot;
+    dev_base = round_up(dev_base + tot, 16);
   }
   CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
   if (byte_off)
@@ -1132,7 +1147,7 @@ int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_byte
     const uint64_t first = n_chunks == 1 ? 0 : c0 * L.channel_len;
     const uint64_t count = n_chunks == 1 ? total : (c1 - c0) * L.channel_len;
     CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
-    rc = decode_pipeline(c, FRONT_DEGA, d_payload, d_bits + s0, d_boff + s0, Lk, max_len, params, d_samples + first, d_nout + s0,
+    rc = decode_pipeline(c, FRONT_DEGA, d_payload, payload_bytes, d_bits + s0, d_boff + s0, Lk, max_len, params, d_samples + first, d_nout + s0,
                          d_status + s0);
     if (rc != DC_OK)
       return rc;
@@ -1154,6 +1169,60 @@ int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_byte
     return DC_ERR_LIBRARY_CALL;
   }
   return DC_OK;
+}
+
+// ---- asynchronous forms of the two host-buffer calls --------------------------------------------------------
+// The call runs on a worker thread owned by the context and dc_wait() joins it.  A context has its own streams, copy
+// engines' queues and staging memory, so an encode on one context (mostly host -> device traffic) and a decode on
+// another (mostly device -> host) use both directions of the PCIe link at once; one context alone is half duplex.
+static int start_worker(dc_ctx *c, std::thread *t)
+{
+  if (!t)
+    return DC_ERR_MEMORY;
+  c->worker = t;
+  return DC_OK;
+}
+
+int dc_dega_encode_host_async(dc_ctx *c, const float *samples, const dc_layout *layout, const dc_params *params, uint8_t *payload,
+                              uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes)
+{
+  if (!c || !params_ok(params) || !layout)
+    return DC_ERR_INVALID_VALUE;
+  if (c->worker)
+    return DC_ERR_INVALID_MODE;   // one call in flight per context
+  const dc_layout lay = *layout;
+  const dc_params par = *params;
+  c->worker_rc = DC_OK;
+  return start_worker(c, new (std::nothrow) std::thread([=]() {
+                        c->worker_rc = dc_dega_encode_host(c, samples, &lay, &par, payload, payload_cap, bit_len, byte_off, status, total_bytes);
+                      }));
+}
+
+int dc_dega_decode_host_async(dc_ctx *c, const uint8_t *payload, uint64_t payload_bytes, const uint64_t *bit_len, const uint64_t *byte_off,
+                              const dc_layout *layout, const dc_params *params, float *samples, uint64_t *n_out, int32_t *status)
+{
+  if (!c || !params_ok(params) || !layout || !bit_len || !byte_off)
+    return DC_ERR_INVALID_VALUE;
+  if (c->worker)
+    return DC_ERR_INVALID_MODE;
+  const dc_layout lay = *layout;
+  const dc_params par = *params;
+  c->worker_rc = DC_OK;
+  return start_worker(c, new (std::nothrow) std::thread([=]() {
+                        c->worker_rc = dc_dega_decode_host(c, payload, payload_bytes, bit_len, byte_off, &lay, &par, samples, n_out, status);
+                      }));
+}
+
+int dc_wait(dc_ctx *c)
+{
+  if (!c)
+    return DC_ERR_INVALID_VALUE;
+  if (!c->worker)
+    return DC_OK;
+  c->worker->join();
+  delete c->worker;
+  c->worker = nullptr;
+  return c->worker_rc;
 }
 
 // ---- LZMH ---------------------------------------------------------------------------------------------------
@@ -1225,11 +1294,12 @@ int dc_lzmh_decode_device(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_
                           const uint64_t *d_byte_off, uint64_t n, uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len,
                           int32_t *d_status)
 {
-  (void)payload_bytes;
   if (!c || !d_bit_len || !d_byte_off || !d_out_off || !d_out_len || !d_status)
     return DC_ERR_INVALID_VALUE;
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
   c->ev_mask = 0;
+  CU_TRY(c, cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), c->stream), DC_ERR_LIBRARY_CALL);
+  launch_validate_index(d_bit_len, d_byte_off, n, payload_bytes, d_status, c->stream);
   LzmhArgs la;
   memset(&la, 0, sizeof(la));
   la.n_streams = n;

@@ -10,7 +10,11 @@
 //
 // Every stream's byte range is byte-identical to the file the reference's DCCLI writes for the same samples and chain,
 // so `dd`-extracting one range and running the reference's `decode ...` chain on it restores that stream
-// (tests/test_container.py does exactly that with oracle/_ref/DCCLI).  Writers are position based (pwrite): the ranks
+// (tests/test_container.py does exactly that with oracle/_ref/DCCLI).
+// One exception: a stream of 0 bits occupies 0 bytes here, while DCCLI's file for it is the single byte 0x00 (its
+// uninit always writes the byte register, bit_file_buffer.c:329-333,312-318).  Only A-XDR of an empty meter and LZMH
+// of an empty or 403-byte block produce 0 bits (lzmh.c:169-173); DEGA never does (an empty input codes to 3 bits).
+// The bit count in the index is what tells such a stream from a one-byte one, which the reference's file cannot.  Writers are position based (pwrite): the ranks
 // of a multi-GPU job write their index and payload slices into the same file at the offsets the size exchange
 // (shard.exchange_sizes) gave them, in any order.
 #include <errno.h>
@@ -58,11 +62,19 @@ static int read_all(int fd, void *buf, uint64_t n, uint64_t off)
   return DC_OK;
 }
 
+// all comparisons are written so that no sum or product of header fields can wrap (the header may come from a corrupt file)
 static bool header_ok(const dc_container_header *h)
 {
-  return memcmp(h->magic, kMagic, 8) == 0 && h->version == DC_CONTAINER_VERSION && h->index_offset >= sizeof(dc_container_header) &&
-         h->payload_offset >= h->index_offset + 8 * h->n_streams && h->chain >= DC_CHAIN_DEGA && h->chain <= DC_CHAIN_LZMH;
+  if (memcmp(h->magic, kMagic, 8) != 0 || h->version != DC_CONTAINER_VERSION || h->chain < DC_CHAIN_DEGA || h->chain > DC_CHAIN_LZMH)
+    return false;
+  if (h->index_offset < sizeof(dc_container_header) || h->payload_offset < h->index_offset)
+    return false;
+  if (h->n_streams > (h->payload_offset - h->index_offset) / 8)
+    return false;
+  return h->payload_bytes <= UINT64_MAX - h->payload_offset;
 }
+
+static bool range_ok(uint64_t first, uint64_t n, uint64_t limit) { return first <= limit && n <= limit - first; }
 
 extern "C" {
 
@@ -112,7 +124,7 @@ int dc_container_create(const char *path, const dc_container_header *h)
 int dc_container_write_shard(const char *path, const dc_container_header *h, uint64_t first_stream, uint64_t n, const uint64_t *bit_len,
                              uint64_t byte_base, const uint8_t *payload, uint64_t payload_bytes)
 {
-  if (!path || !h || !header_ok(h) || first_stream + n > h->n_streams || byte_base + payload_bytes > h->payload_bytes ||
+  if (!path || !h || !header_ok(h) || !range_ok(first_stream, n, h->n_streams) || !range_ok(byte_base, payload_bytes, h->payload_bytes) ||
       (n && !bit_len) || (payload_bytes && !payload))
     return DC_ERR_INVALID_VALUE;
   const int fd = open(path, O_WRONLY);
@@ -143,7 +155,7 @@ int dc_container_read_header(const char *path, dc_container_header *h)
 
 int dc_container_read_index(const char *path, const dc_container_header *h, uint64_t first_stream, uint64_t n, uint64_t *bit_len)
 {
-  if (!path || !h || !header_ok(h) || first_stream + n > h->n_streams || (n && !bit_len))
+  if (!path || !h || !header_ok(h) || !range_ok(first_stream, n, h->n_streams) || (n && !bit_len))
     return DC_ERR_INVALID_VALUE;
   const int fd = open(path, O_RDONLY);
   if (fd < 0)
@@ -155,7 +167,7 @@ int dc_container_read_index(const char *path, const dc_container_header *h, uint
 
 int dc_container_read_payload(const char *path, const dc_container_header *h, uint64_t byte_off, uint64_t nbytes, uint8_t *dst)
 {
-  if (!path || !h || !header_ok(h) || byte_off + nbytes > h->payload_bytes || (nbytes && !dst))
+  if (!path || !h || !header_ok(h) || !range_ok(byte_off, nbytes, h->payload_bytes) || (nbytes && !dst))
     return DC_ERR_INVALID_VALUE;
   const int fd = open(path, O_RDONLY);
   if (fd < 0)

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) csv_compact_kernel(const float *value, co
 static unsigned csv_grid(uint64_t n, unsigned block)
 {
   const uint64_t want = (n + block - 1) / block;
-  return (unsigned)(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16);
+  const uint64_t cap = (uint64_t)sm_count() * 16;
+  return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
 void launch_csv_count(const uint8_t *text, uint64_t n, uint64_t *tile_bits, cudaStream_t st)

@@ -6,12 +6,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "dega_device.cuh"
 
 namespace dc {
 
-static uint64_t g_launches = 0;
-uint64_t launch_counter() { return g_launches; }
+static std::atomic<uint64_t> g_launches{0};   // contexts may run on several host threads (dc_*_host_async)
+uint64_t launch_counter() { return g_launches.load(); }
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
 // Work distribution of the stream-per-thread kernels: a stream is one long sequential task (up to milliseconds), so
@@ -40,17 +42,22 @@ __device__ __forceinline__ void warp_tasks(unsigned int *work, uint64_t n_stream
   }
 }
 
-static int sm_count()
+// SM count of the current device (cached per device: a process may drive several)
+int sm_count()
 {
-  static int n = 0;
-  if (n == 0)
+  static int cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64)
+    dev = 0;
+  if (cached[dev] == 0)
   {
-    int dev = 0;
-    cudaGetDevice(&dev);
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+      n = 148;   // B200
+    cached[dev] = n;
   }
-  return n;
+  return cached[dev];
 }
 
 // grid of a resident launch: ctas_per_sm CTAs on every SM, fewer when there is less work
@@ -417,7 +424,8 @@ void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
     return;
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
-  const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);   // grid-stride over a multiple of the SM count
+  const uint64_t cap = (uint64_t)sm_count() * 16;                                // grid-stride over a multiple of the SM count
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
   const uint64_t total_words = a.n_streams * a.words_per_stream;
   if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.payload_words) & 15) == 0 &&
       a.words_per_stream >= 4 && total_words % 4 == 0 && total_words < (1ull << 32))
@@ -436,7 +444,8 @@ void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
     return;
   const unsigned block = 256;
   const uint64_t want = (total + block - 1) / block;
-  const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
+  const uint64_t cap = (uint64_t)sm_count() * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
   const uint64_t total_samples = a.n_streams * a.len;
   if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.payload) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0 &&
       a.len >= 4 && total_samples % 4 == 0 && total_samples < (1ull << 32))
@@ -488,6 +497,7 @@ void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len
 static const int kBacThreads = 1024;
 
 int bac_smem_bytes() { return kDivTableEntries * (int)sizeof(DivEntry); }
+int bac_threads_per_sm() { return kBacThreads; }
 
 __device__ __forceinline__ void load_div_table(DivEntry *smem, const DivEntry *gmem)
 {
@@ -675,6 +685,29 @@ void launch_byte_scan(const uint64_t *nbits, uint64_t n, uint64_t *byte_off, uin
   scan_totals_kernel<<<1, kScanThreads, 0, st>>>(tile_tmp, n_tiles);
   scan_add_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(byte_off, n, tile_tmp, n_tiles);
   g_launches += 3;
+}
+
+// Decoder-side check of a stream index that came from outside (a container file, a caller's arrays): a stream whose
+// byte range does not lie inside the payload is marked ERROR_INVALID_FORMAT, and the decode kernels skip it instead
+// of reading past the allocation.  Overflow-safe (bit_len and byte_off are arbitrary 64-bit values).
+__global__ void __launch_bounds__(256) validate_index_kernel(const uint64_t *bit_len, const uint64_t *byte_off, uint64_t n, uint64_t payload_bytes,
+                                                             int32_t *status)
+{
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+    return;
+  const uint64_t bits = bit_len[s], off = byte_off[s];
+  const uint64_t nbytes = (bits >> 3) + ((bits & 7) != 0);
+  if (off > payload_bytes || nbytes > payload_bytes - off)
+    status[s] = DC_ERR_INVALID_FORMAT_D;
+}
+
+void launch_validate_index(const uint64_t *bit_len, const uint64_t *byte_off, uint64_t n, uint64_t payload_bytes, int32_t *status, cudaStream_t st)
+{
+  if (n == 0)
+    return;
+  validate_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bit_len, byte_off, n, payload_bytes, status);
+  g_launches++;
 }
 
 // one warp per stream, byte-granular destination

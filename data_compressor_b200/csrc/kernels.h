@@ -135,6 +135,7 @@ struct BacArgs
 void launch_bac_encode(const BacArgs &a, cudaStream_t st);
 void launch_bac_decode(const BacArgs &a, cudaStream_t st);
 int bac_smem_bytes();
+int bac_threads_per_sm();   // streams one SM holds in flight in the coder kernels
 
 // ---- compaction: byte counts -> exclusive scan -> dense payload ---------------------------------------
 // byte_off[n+1] = exclusive scan of ceil(nbits[s] / 8); tile_tmp needs ceil(n / 4096) + 1 uint64.
@@ -142,6 +143,9 @@ void launch_byte_scan(const uint64_t *nbits, uint64_t n, uint64_t *byte_off, uin
 // copies stream s (scratch, fixed stride) to payload + byte_off[s]; streams that do not fit are skipped
 void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t *nbits, const uint64_t *byte_off,
                    uint64_t n, uint8_t *payload, uint64_t payload_cap, cudaStream_t st);
+
+// marks streams whose byte range [byte_off[s], + ceil(bit_len[s] / 8)) leaves the payload with ERROR_INVALID_FORMAT
+void launch_validate_index(const uint64_t *bit_len, const uint64_t *byte_off, uint64_t n, uint64_t payload_bytes, int32_t *status, cudaStream_t st);
 
 // ---- aggregate (granularity reduction): out[c][g] = sum of in[c][g*k .. g*k+k), strictly sequential float32 adds
 void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *out, cudaStream_t st);
@@ -175,6 +179,9 @@ struct LzmhArgs
 };
 void launch_lzmh_encode(const LzmhArgs &a, cudaStream_t st);
 void launch_lzmh_decode(const LzmhArgs &a, cudaStream_t st);
+
+// multiprocessor count of the current device
+int sm_count();
 
 // number of kernel launches issued so far by the launch_* wrappers (process-wide)
 uint64_t launch_counter();

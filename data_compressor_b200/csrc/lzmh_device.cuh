@@ -407,6 +407,12 @@ __device__ inline void lzmh_decode_warp(const LzmhArgs &a, const uint64_t s, con
                                         const uint32_t modtab)
 {
   const uint32_t lane = threadIdx.x & 31;
+  if (a.status[s] != 0)   // marked by the index check (its byte range leaves the payload): nothing is read
+  {
+    if (lane == 0)
+      a.out_len[s] = 0;
+    return;
+  }
   LzWarpBits r;
   const uint64_t nbits = a.bits_in.nbits[s];
   r.init(src_ptr(a.bits_in, s), nbits, lane);

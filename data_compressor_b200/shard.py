@@ -38,6 +38,38 @@ def exchange_sizes(total_bytes: int, n_streams: int, device, group=None) -> dict
     }
 
 
+class PendingSizes:
+    """The size exchange in flight: started right after a rank's encode, resolved when the container offsets are needed
+    (so the collective and the copy of its 16 bytes per rank overlap whatever the rank does next, e.g. the decode of a
+    round-trip benchmark, instead of stalling the step)."""
+
+    def __init__(self, rank, world, gathered, work):
+        self.rank, self.world, self.gathered, self.work = rank, world, gathered, work
+
+    def result(self) -> dict:
+        if self.work is not None:
+            self.work.wait()
+        allv = self.gathered.view(self.world, 2).cpu()
+        sizes, counts = allv[:, 0].tolist(), allv[:, 1].tolist()
+        return {
+            "rank": self.rank, "world": self.world, "sizes": sizes, "counts": counts,
+            "byte_base": sum(sizes[:self.rank]), "stream_base": sum(counts[:self.rank]),
+            "total_bytes": sum(sizes), "total_streams": sum(counts),
+        }
+
+
+def exchange_sizes_async(total_bytes: int, n_streams: int, device, group=None) -> PendingSizes:
+    """Starts the all-gather of (payload bytes, stream count); PendingSizes.result() gives exchange_sizes' dict."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = torch.tensor([int(total_bytes), int(n_streams)], dtype=torch.int64, device=device)
+    if world == 1:
+        return PendingSizes(rank, world, mine, None)
+    flat = torch.empty(world * 2, dtype=torch.int64, device=device)
+    work = dist.all_gather_into_tensor(flat, mine, group=group, async_op=True)
+    return PendingSizes(rank, world, flat, work)
+
+
 def global_byte_offsets(local_byte_off: torch.Tensor, byte_base: int) -> torch.Tensor:
     """Container-wide offsets of this rank's streams: local exclusive scan + the rank's base."""
     return local_byte_off + int(byte_base)

@@ -72,3 +72,15 @@ def watts_u16(n_channels: int, n_samples: int, device="cpu", seed: int = 0xDC000
     lo = (w & 0xFF).to(torch.uint8)
     hi = (w >> 8).to(torch.uint8)
     return torch.stack((lo, hi), dim=2).reshape(n_channels, 2 * n_samples).contiguous()
+
+
+def lzmh_blocks(n_blocks: int, block_bytes: int = 65536, device="cpu", seed: int = 0xDC0000) -> torch.Tensor:
+    """uint8 [n_blocks * block_bytes]: the watts_u16 profiles cut into LZMH blocks (config 4), with one adjustment the
+    survey asks for: no block ends in a zero byte.  The reference's decoder drops trailing zero-valued literals whose bits
+    sit in its 32-bit window when the input ends (lzmh.c:571; `"A\0"` decodes to `"A"`), so such a block does not
+    round-trip through the REFERENCE either; a last high byte of 0 (a reading below 256 W) becomes 1."""
+    per_channel = 2 * 86400
+    chans = (n_blocks * block_bytes + per_channel - 1) // per_channel
+    data = watts_u16(chans, 86400, device=device, seed=seed).reshape(-1)[: n_blocks * block_bytes].contiguous()
+    data.view(n_blocks, block_bytes)[:, -1].clamp_(min=1)
+    return data

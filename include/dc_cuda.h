@@ -79,6 +79,10 @@ int  dc_synchronize(dc_ctx *ctx);
 void *dc_stream(dc_ctx *ctx);
 /* Number of kernel launches issued through this context since creation. */
 uint64_t dc_launch_count(const dc_ctx *ctx);
+/* How many streams the arithmetic-coder kernels keep in flight at once on this device (SM count x resident threads
+   per SM; one stream per thread).  A batch whose stream count is a multiple of this runs in whole waves; callers that
+   are free to pick a block length (the reference has no block parameter at all, DCLib/src/enc_dec.c:51-60) can use it. */
+uint64_t dc_coder_wave_streams(dc_ctx *ctx);
 
 /* Per-kernel device timing (CUDA events on the context's stream around every launch).  The reference's
    analogue is the per-stage "Time elapsed" print of DCCLI (DCCLI/src/cli.c:338-352,444-459). */
@@ -134,6 +138,22 @@ int dc_dega_decode_host(dc_ctx *ctx, const uint8_t *payload, uint64_t payload_by
                         const uint64_t *bit_len, const uint64_t *byte_off,
                         const dc_layout *layout, const dc_params *params,
                         float *samples, uint64_t *n_out, int32_t *status);
+
+/* Asynchronous forms of the two calls above: same arguments and results, but the call returns at once and the work
+   (copies in, kernels, copies out) proceeds on a worker thread owned by the context; dc_wait() blocks until it is
+   done and returns its code.  One call in flight per context (a second one returns DC_ERR_INVALID_MODE); every buffer
+   and *total_bytes must stay valid until dc_wait() returns; layout and params are copied.  The reason to use them: one
+   call keeps one direction of the PCIe link busy (an encode is mostly host -> device, a decode mostly device ->
+   host), so an encode on one context running next to a decode on another uses the link full duplex.  The reference
+   has no analogue (one DCCLI process per stream, DCCLI/src/cli.c:407-473); its unit of overlap is the process. */
+int dc_dega_encode_host_async(dc_ctx *ctx, const float *samples, const dc_layout *layout, const dc_params *params,
+                              uint8_t *payload, uint64_t payload_cap,
+                              uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes);
+int dc_dega_decode_host_async(dc_ctx *ctx, const uint8_t *payload, uint64_t payload_bytes,
+                              const uint64_t *bit_len, const uint64_t *byte_off,
+                              const dc_layout *layout, const dc_params *params,
+                              float *samples, uint64_t *n_out, int32_t *status);
+int dc_wait(dc_ctx *ctx);
 
 /* ---- batch face: A-XDR = normalize only ---------------------------------------------------- */
 /* `encode normalize` (normalize.c:9-27) for every stream: stream s becomes len(s) * value_size_bits

@@ -71,6 +71,50 @@ def test_container_rejects_foreign_and_truncated_files(tmp_path):
         ct.write_shard(p, h, 3, np.zeros(2, np.uint64), 0, np.zeros(1, np.uint8))     # index slice past the end
 
 
+def test_container_header_fields_cannot_wrap(tmp_path):
+    """Corrupt headers whose sums would wrap 64 bits are rejected, as are slices given with wrapping arguments."""
+    import ctypes as C
+    from data_compressor_b200 import DcError, _lib, container as ct
+    lib = _lib.load()
+    p = str(tmp_path / "c.dcb")
+    h = ct.make_header(ct.CHAIN_DEGA, 4, 100, 1, 40, 10)
+    ct.create(p, h)
+    raw = bytearray(open(p, "rb").read())
+    for field, value in (("n_streams", (1 << 61) + 1), ("payload_bytes", (1 << 64) - 8), ("index_offset", (1 << 64) - 64)):
+        g = _lib.ContainerHeader.from_buffer_copy(bytes(raw[:128]))
+        setattr(g, field, value)
+        q = str(tmp_path / f"bad_{field}")
+        open(q, "wb").write(bytes(g) + bytes(raw[128:]))
+        with pytest.raises(DcError):
+            ct.read_header(q)
+        assert lib.dc_container_read_index(os.fsencode(q), C.byref(g), 0, 1, np.zeros(1, np.uint64).ctypes.data) == -1
+    buf = np.zeros(4, np.uint64)
+    assert lib.dc_container_read_index(os.fsencode(p), C.byref(h), (1 << 64) - 1, 2, buf.ctypes.data) == -1
+    assert lib.dc_container_read_payload(os.fsencode(p), C.byref(h), (1 << 64) - 4, 8, buf.ctypes.data) == -1
+    assert lib.dc_container_write_shard(os.fsencode(p), C.byref(h), 2, (1 << 64) - 1, buf.ctypes.data, 0, None, 0) == -1
+
+
+def test_load_encoded_checks_the_index_against_the_payload(oracle, tmp_path):
+    """An index whose byte counts do not add up to the header's payload size is refused before any decoder sees it."""
+    torch = pytest.importorskip("torch")
+    from data_compressor_b200 import DcError, container as ct
+    rng = np.random.default_rng(3)
+    x = _profiles(rng, 2, 300)
+    streams, pays, bits = _oracle_encode(oracle, x, 100)
+    payload = np.frombuffer(b"".join(pays), dtype=np.uint8)
+    path = str(tmp_path / "d.dcb")
+    h = ct.make_header(ct.CHAIN_DEGA, len(streams), payload.size, 2, 300, 100)
+    ct.create(path, h)
+    ct.write_shard(path, h, 0, bits, 0, payload)
+    enc, g = ct.load_encoded(path, device="cpu")
+    assert enc.total_bytes == payload.size and np.array_equal(enc.bit_len.numpy().astype(np.uint64), bits)
+    bad = bits.copy()
+    bad[2] += 4096
+    ct.write_shard(path, h, 0, bad, 0, payload)
+    with pytest.raises(DcError):
+        ct.load_encoded(path, device="cpu")
+
+
 def test_stream_cut_out_of_the_container_decodes_with_the_reference_cli(oracle, tmp_path):
     """dd one stream out of the container, run the reference's own DCCLI decode chain on it: the samples come back."""
     cli = ob.REF_CLI

@@ -342,14 +342,21 @@ def test_lzmh_batch_blocks(ctx, oracle):
 
 
 # ---- full size: BASELINE.json config 2 (4096 channels x 1 day), size-independent properties ------------------
-def test_full_size_round_trip_and_spot_checks(ctx, oracle):
+@pytest.mark.parametrize("block_len", [1024, "bench"])
+def test_full_size_round_trip_and_spot_checks(ctx, oracle, block_len):
+    """The configuration bench.py runs ("bench" = the block length it derives from the device, 1168 on a 148-SM B200)
+    and the 1024-sample blocks next to it: round trip of all samples, container invariants, oracle spot checks."""
     from data_compressor_b200 import synth
-    nc, cl, bl = 4096, 86400, 1024
+    nc, cl = 4096, 86400
+    bl = ctx.two_wave_block_len(nc, cl) if block_len == "bench" else block_len
+    per = -(-cl // bl)
     x = synth.redd_like(nc, cl, device="cuda")
     enc = ctx.dega_encode(x, block_len=bl)
     assert not enc.status.any().item()
     n = enc.n_streams
-    assert n == nc * 85
+    assert n == nc * per
+    if block_len == "bench":
+        assert n <= 2 * ctx.coder_wave_streams() < n + nc        # two waves, as full as whole blocks per channel allow
     # container invariants: offsets are the exclusive scan of the byte counts
     nbytes = (enc.bit_len + 7) // 8
     assert torch.equal(enc.byte_off[1:], torch.cumsum(nbytes, 0)) and int(enc.byte_off[0]) == 0
@@ -361,19 +368,175 @@ def test_full_size_round_trip_and_spot_checks(ctx, oracle):
     assert not status.any().item()
     assert torch.equal(y.view(torch.int32), x.view(torch.int32))
     del y
-    # spot-check 24 random (channel, block) streams bit for bit against the oracle
+    # spot-check random (channel, block) streams, and the ragged last block of a channel, bit for bit against the oracle
     rng = np.random.default_rng(0)
-    for s in rng.integers(0, n, 24):
-        c, b = divmod(int(s), 85)
+    for s in list(rng.integers(0, n, 24)) + [per - 1, n - 1]:
+        c, b = divmod(int(s), per)
         xs = x[c, b * bl:(b + 1) * bl].cpu().numpy()
         rc, want, nb = oracle.dega_encode(xs)
         assert rc == 0 and nb == int(enc.bit_len[s]) and enc.stream_bytes(int(s)) == want
-    # whole-channel streams (parity with one plain DCCLI run per channel), on a slice
-    enc2 = ctx.dega_encode(x[:64].contiguous(), block_len=0)
-    rc, want, nb = oracle.dega_encode(x[5].cpu().numpy())
-    assert enc2.stream_bytes(5) == want and int(enc2.bit_len[5]) == nb
-    y2, _, _ = ctx.dega_decode(enc2)
-    assert torch.equal(y2.view(torch.int32), x[:64].view(torch.int32))
+
+
+def test_whole_channel_streams_at_config_2_length(ctx, oracle):
+    """block_len = 0: one stream per channel-day, the reference's own unit of work (one plain DCCLI run per channel,
+    DCCLI/src/cli.c:430-466); 64 channels of the config-2 generator, every one compared with the oracle."""
+    from data_compressor_b200 import synth
+    x = synth.redd_like(64, 86400, device="cuda", seed=0xDC0000 + 640)
+    enc = ctx.dega_encode(x, block_len=0)
+    assert enc.n_streams == 64 and not enc.status.any().item()
+    xs = x.cpu().numpy()
+    for c in range(64):
+        rc, want, nb = oracle.dega_encode(xs[c])
+        assert rc == 0 and int(enc.bit_len[c]) == nb and enc.stream_bytes(c) == want, c
+    y, n_out, status = ctx.dega_decode(enc)
+    assert torch.equal(y.view(torch.int32), x.view(torch.int32)) and (n_out == 86400).all().item()
+
+
+def test_lzmh_config_4_size_spot_checks(ctx, oracle):
+    """BASELINE.json configs[3] at the bench's size: 16 384 blocks of 64 KiB (1 GiB); every block must come back, 32
+    random blocks are compared with the oracle both ways."""
+    from data_compressor_b200 import synth
+    n_blocks, block = 16384, 65536
+    data = synth.lzmh_blocks(n_blocks, block, device="cuda")
+    payload, bit_len, byte_off, status, total, in_off = ctx.lzmh_encode(data, block_bytes=block)
+    assert not status.any().item() and total == int(byte_off[-1])
+    out, out_len, st2 = ctx.lzmh_decode(payload, total, bit_len, byte_off, in_off)
+    assert not st2.any().item() and (out_len == block).all().item()       # no block ends in an un-ranked zero byte (synth.lzmh_blocks)
+    assert torch.equal(out, data)
+    rng = np.random.default_rng(4)
+    for s in rng.integers(0, n_blocks, 32):
+        s = int(s)
+        blk = data[s * block:(s + 1) * block].cpu().numpy()
+        rc, want, nb = oracle.run_chain([ob.LZMH_ENC], blk, blk.size * 8)
+        o = int(byte_off[s])
+        assert rc == 0 and nb == int(bit_len[s]) and payload[o:o + len(want)].cpu().numpy().tobytes() == want, s
+        rc, back, nb2 = oracle.run_chain([ob.LZMH_DEC], want, nb, out_cap=block + 1024)
+        assert rc == 0 and back == blk.tobytes()
+
+
+# ---- regressions for the round-1 review ------------------------------------------------------------------------
+def test_negative_normalization_factor_fails_like_the_reference(ctx, oracle):
+    """normalization_factor is an unrestricted float option (DCLib/src/enc_dec.c:64-73): with a negative one the
+    normalised values are negative and `encode diff` rejects them (diff.c:15-18).  The fused front end must not take
+    its unsigned fast prefix for such samples."""
+    rng = np.random.default_rng(9)
+    x = profile(rng, (6, 300))
+    x[2, :] = 0.0                   # zeros stay zero whatever the factor
+    x[4, :] = 0.001                 # |x * nf| < 0.5: truncates to 0, no error
+    for nf in (-100.0, -1.0, -0.5):
+        enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=100, nf=nf)
+        st = enc.status.cpu().numpy()
+        for s, xs in enumerate(split_streams(x, 100)):
+            rc, want, nb = oracle.dega_encode(xs, nf=nf)
+            assert st[s] == rc, (nf, s)
+            if rc == 0:
+                assert enc.stream_bytes(s) == want and int(enc.bit_len[s]) == nb, (nf, s)
+        for row in (0, 2, 4):
+            rc, out, nb = ctx.stage_run(DEGA_ENC, x[row], None, 32, nf, True)
+            want = oracle.run_chain(ob.DEGA_ENC, x[row], 300 * 32, 32, nf, 1)
+            assert rc == want[0] and (rc != 0 or (rc, out, nb) == want), (nf, row)
+
+
+def test_chain_buffers_survive_a_growing_staging_block(ctx, oracle):
+    """dc_chain_run_host's ping-pong buffers and the staging block of the *_host calls are separate allocations:
+    alternating the two with growing sizes must neither free nor reuse one for the other."""
+    rng = np.random.default_rng(12)
+    for n in (500, 40000, 2000, 300000, 1000):
+        x = profile(rng, n)
+        want = oracle.run_chain(ob.DEGA_ENC, x, n * 32, 32, 100.0, 1)
+        got = ctx.chain_run(ob.DEGA_ENC, x, None, 32, 100.0, True)
+        assert got[:3] == want, n
+        big = profile(rng, (8, 4 * n))
+        payload, bit_len, byte_off, status = ctx.dega_encode_host(big, block_len=0)
+        assert not status.any()
+        got = ctx.chain_run(ob.DEGA_ENC, x, None, 32, 100.0, True)
+        assert got[:3] == want, n
+        assert payload[int(byte_off[3]):int(byte_off[4])].tobytes() == oracle.dega_encode(big[3])[1]
+
+
+def test_host_encode_many_chunks_with_unaligned_totals(ctx, oracle, monkeypatch):
+    """Many small chunks whose payload sizes are not multiples of 16, pinned output buffers (so the copies back are
+    really asynchronous): a chunk's payload must not land on the tail of the one before it on the device."""
+    from data_compressor_b200 import synth
+    monkeypatch.setenv("DC_HOST_CHUNK_STREAMS", "64")
+    nc, cl, bl = 31, 1000, 40              # 775 streams -> 12 chunks of 2-3 channels
+    x = synth.redd_like(nc, cl, device="cpu", seed=5).numpy()
+    for rep in range(3):
+        payload, bit_len, byte_off, status = ctx.dega_encode_host(x, block_len=bl)
+        assert not status.any() and int(byte_off[-1]) == payload.size
+        streams = split_streams(x, bl)
+        for s, xs in enumerate(streams):
+            want = oracle.dega_encode(xs)[1]
+            o = int(byte_off[s])
+            assert payload[o:o + len(want)].tobytes() == want, (rep, s)
+        y, n_out, st2 = ctx.dega_decode_host(payload, bit_len, byte_off, nc, cl, bl)
+        assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not st2.any()
+
+
+def test_decoders_reject_an_index_that_leaves_the_payload(ctx, oracle):
+    """A truncated / corrupt stream index (byte range outside the payload) gives ERROR_INVALID_FORMAT for that stream,
+    not a read past the allocation; the other streams still decode."""
+    from data_compressor_b200.codec import Encoded
+    rng = np.random.default_rng(21)
+    x = profile(rng, (12, 400))
+    enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=100)
+    n = enc.n_streams
+    bad_off = enc.byte_off.clone()
+    bad_off[7] = enc.total_bytes + (1 << 40)          # far outside
+    bad_len = enc.bit_len.clone()
+    bad_len[20] = (enc.total_bytes + 5) * 8           # runs past the end
+    bad_len[21] = -1                                   # 2^64 - 1 bits
+    bad = Encoded(enc.payload, bad_len, bad_off, enc.status, enc.total_bytes, enc.n_channels, enc.channel_len, enc.block_len)
+    y, n_out, status = ctx.dega_decode(bad)
+    st = status.cpu().numpy()
+    assert st[7] == -3 and st[20] == -3 and st[21] == -3
+    good = np.ones(n, dtype=bool)
+    good[[7, 20, 21]] = False
+    assert not st[good].any()
+    yy = y.cpu().numpy().reshape(-1, 100)
+    assert np.array_equal(yy[good].view(np.uint32), x.reshape(-1, 100)[good].view(np.uint32))
+    # the context is still usable (no sticky CUDA error)
+    y2, _, st2 = ctx.dega_decode(enc)
+    assert not st2.any().item() and torch.equal(y2.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
+    # LZMH: same rule
+    data = torch.from_numpy(rng.integers(0, 7, 5000, dtype=np.uint8)).cuda()
+    payload, bit_len, byte_off, status, total, in_off = ctx.lzmh_encode(data, block_bytes=1000)
+    bo = byte_off.clone()
+    bo[2] = total + 12345
+    out, out_len, st3 = ctx.lzmh_decode(payload, total, bit_len, bo, in_off)
+    assert st3.cpu().tolist() == [0, 0, -3, 0, 0] and int(out_len[2]) == 0
+    assert out[:2000].cpu().numpy().tobytes() == data[:2000].cpu().numpy().tobytes()
+
+
+def test_async_host_calls_on_two_contexts(ctx, oracle):
+    """dc_dega_encode_host_async / dc_dega_decode_host_async / dc_wait: same results as the blocking calls, an encode
+    on one context running next to a decode on another, a second call on a busy context refused."""
+    from data_compressor_b200 import Context, synth
+    nc, cl, bl = 300, 3000, 250
+    x = synth.redd_like(nc, cl, device="cpu", seed=31).numpy()
+    x2 = synth.redd_like(nc, cl, device="cpu", seed=32).numpy()
+    ctx2 = Context(0)
+    try:
+        ref_enc = [np.array(a, copy=True) for a in ctx.dega_encode_host(x, block_len=bl)]
+        ref2 = [np.array(a, copy=True) for a in ctx.dega_encode_host(x2, block_len=bl)]
+        pe = ctx.dega_encode_host(x2, block_len=bl, wait=False, slot=1)
+        par, lay = ctx._params(32, 100.0, True), ctx._layout(nc, cl, bl)
+        import ctypes as C
+        rc = ctx.lib.dc_dega_encode_host_async(ctx.h, x.ctypes.data, C.byref(lay), C.byref(par), None, 0, None, None, None, None)
+        assert rc == -4                                                   # one call in flight per context
+        pd = ctx2.dega_decode_host(ref_enc[0], ref_enc[1], ref_enc[2], nc, cl, bl, wait=False)
+        got2 = pe.wait()
+        y, n_out, st = pd.wait()
+        assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not st.any() and (n_out == bl).all()
+        for a, b in zip(got2, ref2):
+            assert np.array_equal(a, b)
+        s = 1234
+        c, b = divmod(s, cl // bl)
+        want = oracle.dega_encode(x2[c, b * bl:(b + 1) * bl])[1]
+        assert got2[0][int(got2[2][s]):int(got2[2][s]) + len(want)].tobytes() == want
+        assert ctx.lib.dc_wait(ctx.h) == 0                                # nothing in flight: a no-op
+    finally:
+        ctx2.close()
 
 
 # ---- aggregate (granularity reduction, SURVEY 8f-2) ------------------------------------------------------------

@@ -59,6 +59,23 @@ def test_random_streams_vs_oracle(sim, oracle, seed):
         assert back[1] == x.tobytes()
 
 
+@pytest.mark.parametrize("nf", [-100.0, -1.0, -0.25, 0.0])
+def test_fused_front_end_with_non_positive_factors(sim, oracle, nf):
+    """normalization_factor is unrestricted (DCLib/src/enc_dec.c:64-73).  A negative one makes the normalised values
+    negative, which `encode diff` rejects (diff.c:15-18); tiny products truncate to 0 and pass.  The fused front end's
+    unsigned fast prefix must hand such samples to the general path."""
+    rng = np.random.default_rng(7)
+    cases = [np.array([1.0, 2.0, 1.5], dtype=np.float32), np.zeros(40, dtype=np.float32), np.full(40, 0.001, dtype=np.float32),
+             (np.abs(rng.integers(0, 5000, 200)).astype(np.float32) / np.float32(100.0)).astype(np.float32),
+             np.concatenate([np.zeros(9, dtype=np.float32), np.array([0.004, 3.0], dtype=np.float32)])]
+    for x in cases:
+        want = oracle.run_chain(ob.DEGA_ENC, x, x.size * 32, 32, nf, 1)
+        got = sim.stage_run(DEGA_ENC, x, x.size * 32, 32, nf, 1)
+        assert got[0] == want[0], (nf, x[:4])       # a failing chain leaves no defined output
+        if want[0] == 0:
+            assert got == want, (nf, x[:4])
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_bac_random_bits_vs_oracle(sim, oracle, seed):
     rng = np.random.default_rng(50 + seed)
