@@ -402,7 +402,7 @@ def run_ours(args):
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         kw = dict(vs=VS, nf=NF, adaptive=ADAPTIVE)
         ekw = dict(kw, block_len=L_, payload_cap=int(enc.total_bytes * 1.05) + 4096)   # the compressed size is known from the device run
-        ctx2 = Context(local)   # the decoder's context: own streams and staging, so that its copies run beside the encoder's
+        ctx2 = ctx   # one context: its job engine runs an encode and a decode side by side and issues the copies of both itself
         for _ in range(2):   # warm-up: the first calls page-lock ~3.3 GB of host buffers and size the device staging
             for slot in (0, 1):
                 pay, bl, bo, st = ctx.dega_encode_host(hxn, slot=slot, **ekw)
@@ -418,19 +418,37 @@ def run_ours(args):
         barrier()
         dt_serial = (time.perf_counter() - t0) / e2e_steps
         ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all())
-        # (b) two contexts: step i encodes the batch (host -> device heavy) while the payload step i-1 produced is
-        # decoded (device -> host heavy); every step still copies every input in and every result out
-        prev = ctx.dega_encode_host(hxn, slot=0, **ekw)
-        yy2.fill(0)   # the second context's output buffer: the check below must see what the timed steps wrote
+        # (b) streaming: encodes are queued two deep, the decode of step i's payload is queued as soon as that encode has
+        # been collected, and jobs are collected in submission order (dc_wait_next).  The context then always has its next
+        # job at hand: an encode (host -> device heavy) runs next to a decode (device -> host heavy), and the tail of one job
+        # overlaps the head of the next.  Every step copies every input in and every result out; K encodes and K decodes of
+        # every stream in all, pipeline fill and drain inside the timed region.
+        n_pipe = max(e2e_steps, args.e2e_stream_steps)
+
+        def stream_steps(k_steps):
+            """k_steps encodes + k_steps decodes through the queue; returns (seconds, last decode's results, last encode's results, collect times)."""
+            t_start = time.perf_counter()
+            pes = {i: ctx.dega_encode_host(hxn, slot=i % 4, wait=False, **ekw) for i in range(min(2, k_steps))}
+            pds, prev_, stamps = [], None, []
+            for i in range(k_steps):
+                prev_ = pes.pop(i).wait()
+                stamps.append(time.perf_counter() - t_start)
+                pds.append(ctx.dega_decode_host(prev_[0], prev_[1], prev_[2], C_, S_, L_, wait=False, **kw))
+                if i + 2 < k_steps:
+                    pes[i + 2] = ctx.dega_encode_host(hxn, slot=(i + 2) % 4, wait=False, **ekw)
+            for pd in pds:
+                last = pd.wait()
+            barrier()
+            return time.perf_counter() - t_start, last, prev_, stamps
+
+        for slot in (2, 3):   # four sets of encode outputs: encode i+2 may start while the payload of step i-1 is still being decoded
+            ctx.dega_encode_host(hxn, slot=slot, **ekw)
+        stream_steps(4)       # warm-up of the streaming pattern itself: the second staging block of each kind is allocated here
+        yy2.fill(0)           # the decoder's output buffer: the check below must see what the timed steps wrote
         barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            pe = ctx.dega_encode_host(hxn, slot=(i + 1) % 2, wait=False, **ekw)
-            pd = ctx2.dega_decode_host(prev[0], prev[1], prev[2], C_, S_, L_, wait=False, **kw)
-            prev = pe.wait()
-            yy, n_out, st2 = pd.wait()
-        barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
+        dt_all, (yy, n_out, st2), prev, stamps = stream_steps(n_pipe)
+        dt = dt_all / n_pipe
+        steady = (stamps[-1] - stamps[len(stamps) // 2]) / (len(stamps) - 1 - len(stamps) // 2) if len(stamps) > 3 else None
         gc.enable()
         ok = ok and bool((yy.view("uint32") == hxn.view("uint32")).all()) and not bool(st2.any()) and not bool(prev[3].any())
         pay = prev[0]
@@ -470,16 +488,16 @@ def run_ours(args):
         meta = n_streams * (8 + 8 + 4) + 8
         e2e = {"value": world * raw_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(raw_bytes + pay.size + meta), "d2h_bytes_per_step": int(raw_bytes + pay.size + 2 * meta),
-               "api": "dc_dega_encode_host_async on one context + dc_dega_decode_host_async on a second one, dc_wait on both (include/dc_cuda.h); "
-                      "host buffers, every copy inside the timed region; step i encodes the batch while the payload of step i-1 is decoded, "
-                      "so one encode and one decode of every stream complete per step and both PCIe directions carry data at once",
+               "api": "dc_dega_encode_host_async + dc_dega_decode_host_async queued on one context, collected in order with dc_wait_next (include/dc_cuda.h); "
+                      "host buffers, every copy inside the timed region (pipeline fill and drain too); the encode of step i runs next to the decode of the "
+                      "payload step i-1 produced, so both PCIe directions carry data at once; K encodes + K decodes of every stream in K steps",
+               "steps": n_pipe, "steady_state_ms_per_step": steady * 1e3 if steady else None,
                "serial_value": world * raw_bytes / dt_serial / 1e9, "serial_ms_per_step": dt_serial * 1e3,
                "serial_api": "dc_dega_encode_host then dc_dega_decode_host on one context (each call uses one direction of the link)",
                "pcie_floor_ms": floor_duplex * 1e3, "pcie_floor_serial_ms": floor_serial * 1e3,
                "pcie_floor_note": f"pinned cudaMemcpyAsync of the same byte counts ({n_in} B each way), no kernels, measured on every rank at once (max over ranks): "
                                   "both directions together / one after the other",
                "frac_of_pcie_floor": floor_duplex / dt, "host_cpus_bound": numa_cpus}
-        ctx2.close()
 
     if rank != 0:
         if world > 1:
@@ -808,6 +826,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the 1024-sample-block and whole-channel figures")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU-baseline work per core")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-stream-steps", type=int, default=20, help="steps of the streaming end-to-end measurement (fill and drain are inside the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="dega", choices=["dega", "axdr", "lzmh", "sweep", "csv"],

@@ -84,6 +84,7 @@ SYMBOLS = {
     "dc_dega_encode_host_async": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
     "dc_dega_decode_host_async": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
     "dc_wait": (_I, [_P]),
+    "dc_wait_next": (_I, [_P]),
     "dc_axdr_encode_device": (_I, [_P, _P, _PL, _PP, _P, _U64, _P, _P, _P, _PU64]),
     "dc_axdr_decode_device": (_I, [_P, _P, _U64, _P, _P, _PL, _PP, _P, _P, _P]),
     "dc_lzmh_encode_device": (_I, [_P, _P, _P, _U64, _P, _U64, _P, _P, _P, _PU64]),

@@ -41,14 +41,21 @@ class Encoded:
 
 
 class Pending:
-    """A *_host_async call in flight on a context; wait() joins it (dc_wait) and returns what the blocking call returns."""
+    """A *_host_async job queued on a context.  Jobs are collected in submission order (dc_wait_next): wait() first
+    collects the jobs queued before this one, then this one, and returns what the blocking call returns."""
 
     def __init__(self, ctx, what, result, keep=()):
-        self.ctx, self.what, self.result, self.keep = ctx, what, result, keep   # keep: the buffers the worker reads
+        self.ctx, self.what, self.result, self.keep = ctx, what, result, keep   # keep: the buffers the job reads
+        self.rc = None
+        ctx.__dict__.setdefault("_pending", []).append(self)
 
     def wait(self):
-        self.ctx._check(self.ctx.lib.dc_wait(self.ctx.h), self.what)
-        self.keep = ()
+        q = self.ctx._pending
+        while self.rc is None:
+            head = q.pop(0)
+            head.rc = int(self.ctx.lib.dc_wait_next(self.ctx.h))
+            head.keep = ()
+        self.ctx._check(self.rc, self.what)
         return self.result()
 
 

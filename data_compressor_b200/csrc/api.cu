@@ -5,9 +5,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -32,15 +36,14 @@ struct dc_ctx
   uint64_t stage_size;
   uint8_t *chain[2];     // intermediate results of dc_chain_run_host (ping-pong), grown on demand
   uint64_t chain_size[2];
-  cudaStream_t s_h2d, s_d2h;          // copy engines of the host-buffer calls (overlap with the compute stream)
-  cudaEvent_t ev_in[kMaxHostChunks], ev_out[kMaxHostChunks];    // per-chunk "input landed" / "results ready"
+  cudaStream_t s_h2d, s_d2h;          // the copy streams of the host-buffer calls: every copy in / every copy out of every job
   uint64_t *h_pinned;   // small pinned mailbox for device->host scalars
   uint64_t launches_base;
   int profiling;
   cudaEvent_t ev[2 * DC_K_COUNT];
   uint32_t ev_mask;   // kernels timed during the last call
-  std::thread *worker;   // the *_host_async call in flight (at most one per context), joined by dc_wait
-  int worker_rc;
+  struct JobEngine *eng;                    // worker thread + queue of the host-buffer calls (see "the job engine")
+  std::vector<struct HostJob *> *async_jobs;   // *_host_async jobs not yet collected by dc_wait
   char err[256];
 };
 
@@ -66,6 +69,22 @@ void set_err(dc_ctx *c, const char *fmt, ...)
   } while (0)
 
 uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// DC_TRACE=1: host-side timeline of the host-buffer calls on stderr (which call, which chunk, when), for finding out what
+// two contexts working side by side wait for
+bool trace_on()
+{
+  static const bool on = getenv("DC_TRACE") != nullptr;
+  return on;
+}
+void trace(const dc_ctx *c, const char *what, int k = -1)
+{
+  if (!trace_on())
+    return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  fprintf(stderr, "[dc %p %10.3f ms] %s %d\n", (const void *)c, ms, what, k);
+}
 
 // RAII: CUDA events around one kernel group when profiling is on
 struct Timed
@@ -330,14 +349,17 @@ int axdr_fast_decode(dc_ctx *c, const uint8_t *d_payload, uint64_t payload_bytes
 // ---- encode pipeline: front end -> [bac] -> scan -> gather ----------------------------------------------
 enum FrontKind { FRONT_DEGA, FRONT_AXDR };
 
+// pub == nullptr: blocking; runs again with a larger coder scratch if a stream outgrew it, returns the total.
+// pub != nullptr: one pass with the scratch factor `boost0`, nothing is waited for; the overflow flag and the total
+// appear in pub[0..1] (mapped host memory) once the stream has got there (the job engine reads them after an event).
 int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Layout &L, uint64_t max_len, const dc_params *p,
                     uint8_t *d_payload, uint64_t payload_cap, uint64_t *d_bit_len, uint64_t *d_byte_off, int32_t *d_status,
-                    uint64_t *total_bytes)
+                    uint64_t *total_bytes, uint64_t *pub = nullptr, unsigned boost0 = 1)
 {
   const uint64_t n = L.n_streams;
   const uint32_t vs = p->value_size_bits;
   c->ev_mask = 0;
-  for (unsigned boost = 1;; boost *= 8)
+  for (unsigned boost = boost0;; boost *= 8)
   {
     const uint64_t front_cap = kind == FRONT_DEGA ? seg_cap_bytes(max_len, vs) : fixed_cap_bytes(max_len, vs);
     const uint64_t bac_cap = kind == FRONT_DEGA ? bac_cap_bytes(front_cap, p->adaptive, boost) : 0;
@@ -423,6 +445,11 @@ int encode_pipeline(dc_ctx *c, FrontKind kind, const float *d_samples, const Lay
     }
     if ((rc = check_launch(c, "gather_kernel")) != DC_OK)
       return rc;
+    if (pub)
+    {
+      launch_publish(d_flags, d_byte_off + n, pub, c->stream);
+      return check_launch(c, "publish_kernel");
+    }
     // one synchronisation per call: total size + overflow flag
     CU_TRY(c, cudaMemcpyAsync(d_flags + 1, d_byte_off + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream), DC_ERR_LIBRARY_CALL);
     uint64_t host_flags[2];
@@ -528,6 +555,9 @@ int decode_pipeline(dc_ctx *c, FrontKind kind, const uint8_t *d_payload, uint64_
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
+static int engine_create(dc_ctx *c);
+static void engine_destroy(dc_ctx *c);
+
 extern "C" {
 
 int dc_abi_version(void) { return DC_ABI_VERSION; }
@@ -572,11 +602,8 @@ int dc_create(dc_ctx **out, int device)
       dc_destroy(c);
       return DC_ERR_LIBRARY_INIT;
     }
-  bool aux_ok = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; i < kMaxHostChunks && aux_ok; i++)
-    aux_ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+  const bool aux_ok = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess && engine_create(c) == DC_OK;
   if (!aux_ok)
   {
     cudaGetLastError();
@@ -592,8 +619,8 @@ void dc_destroy(dc_ctx *c)
 {
   if (!c)
     return;
-  dc_wait(c);
   cudaSetDevice(c->device);
+  engine_destroy(c);   // finishes what is queued, stops the worker
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   if (c->arena)
@@ -612,13 +639,6 @@ void dc_destroy(dc_ctx *c)
   for (int i = 0; i < 2 * DC_K_COUNT; i++)
     if (c->ev[i])
       cudaEventDestroy(c->ev[i]);
-  for (int i = 0; i < kMaxHostChunks; i++)
-  {
-    if (c->ev_in[i])
-      cudaEventDestroy(c->ev_in[i]);
-    if (c->ev_out[i])
-      cudaEventDestroy(c->ev_out[i]);
-  }
   if (c->s_h2d)
     cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h)
@@ -927,17 +947,242 @@ int dc_csv_encode_host(dc_ctx *c, const float *values, uint64_t n, uint32_t colu
   return DC_OK;
 }
 
-// ---- DEGA, host buffers ----------------------------------------------------------------------------------
-// Channel chunks of the host-buffer calls: the copy of chunk k+1 (and the copy-back of chunk k-1) overlaps the kernels
-// of chunk k.  These calls are bound by the PCIe copies (1.4 GB in, 0.5 GB out for config 2 against ~15 ms of kernels),
-// so chunks are sized for copy overlap rather than for full coder waves: a quarter wave (37 888 streams) still gives
-// every SM eight warps through the warp-task scheduler, and eight chunks expose only 1/8 of the first copy in and of
-// the last copy out.  Ragged layouts use one chunk.
+// ---- DEGA, host buffers: the job engine ---------------------------------------------------------------------
+// A host-buffer call is a JOB: its channels are cut into chunks, and every chunk goes through copy in -> kernels -> copy
+// out.  One worker thread per context runs the jobs; at most one encode and one decode are in flight at a time, each on
+// its own compute stream with its own scratch (a "lane"), and ALL copies of both go through one host->device stream and
+// one device->host stream, in the order the worker issues them.  That order is the point:
+//   * an encode is mostly host->device traffic, a decode mostly device->host, so the two together use the PCIe link full
+//     duplex (measured on this pool: 1.4 GB one way 25.5 ms, 1.4 GB each way at once 28.5 ms);
+//   * left to the hardware -- two contexts with their own copy streams -- the two calls do NOT overlap: a copy stream
+//     that always has its next copy queued keeps the engine (the other call's first 62 MB copy landed after the first
+//     call's last one, 30 ms later), and a copy that waits for an event blocks ready copies queued behind it, including
+//     the 16-byte read-back of a chunk's size (profiles/r2_e2e_trace.txt).  So the worker only ever issues copies that
+//     are READY (a chunk's results are issued after its kernels have finished, never behind an event), cuts every copy
+//     into pieces of 32 MB and keeps only three of them in flight per direction, so that it decides every ~0.6 ms
+//     whose piece goes next -- host -> device: the decode's first (its payload is a third of the bytes and unlocks
+//     the long copy back), device -> host: in turns -- and reads a chunk's payload size from mapped host memory
+//     (publish_kernel) instead of through a copy.
+// Chunk size: the coder kernels run one stream per thread, so a chunk needs about half a wave of streams
+// (dc_coder_wave_streams) to keep the schedulers busy; smaller chunks hide more of the first copy in and the last copy
+// out but their kernels are latency bound (a quarter-wave chunk takes 3 ms instead of 1), and the encode and decode
+// kernels cannot share an SM (each takes its whole register file).
+static const int kJobKinds = 2;   // 0: encode jobs, 1: decode jobs; one lane (compute stream + scratch) each
+static const int kJobSlots = 4;   // two jobs per kind can be in flight (slot = 2 * kind + buffer): the second one is admitted
+                                  // when every upload of the first has been issued, so that its uploads fill the time the
+                                  // first one spends on its last kernels and its last copy back (6 ms per job otherwise)
+
+struct HostJob
+{
+  int kind;   // 0 encode, 1 decode
+  const float *samples_in;
+  float *samples_out;
+  const uint8_t *payload_in;
+  uint8_t *payload_out;
+  uint64_t payload_size;   // capacity (encode) / bytes (decode)
+  const uint64_t *bit_len_in, *byte_off_in;
+  uint64_t *bit_len_out, *byte_off_out;
+  int32_t *status;
+  uint64_t *n_out, *total_bytes;
+  dc_layout layout;
+  dc_params params;
+  int rc;
+  bool done;
+};
+
+struct Lane   // what the kernel pipelines take from the context: swapped in while a job's chunk is launched
+{
+  cudaStream_t stream;
+  uint8_t *arena;
+  uint64_t arena_size;
+  unsigned int *d_work;
+};
+
+struct Piece   // one copy of at most kPieceBytes; `after` (if set) is recorded behind it
+{
+  void *dst;
+  const void *src;
+  uint64_t bytes;
+  cudaEvent_t after;
+};
+static const uint64_t kPieceBytes = 32ull << 20;
+static const int kPiecesInFlight = 3;   // per direction: ~2 ms of copies queued, so a piece that becomes ready never waits longer than that
+
+struct CopyDir   // one direction of the link: its stream and the markers of the pieces in flight
+{
+  cudaStream_t stream;
+  cudaMemcpyKind kind;
+  cudaEvent_t ring[8];
+  int head, count;
+  int turn;   // device -> host: whose piece goes next when both jobs have one
+};
+
+struct JobRun   // a job admitted to its slot
+{
+  HostJob *job;
+  int slot;
+  uint64_t age;   // admission number: within a kind the older job goes first everywhere
+  std::deque<Piece> h2d, d2h;   // copies decided on, not yet handed to the copy streams
+  int up_issued, out_issued;    // chunks whose last upload piece / last result piece has been issued (its event recorded)
+  Layout L;
+  uint64_t max_len, total, n, bpc;
+  int n_chunks;
+  uint64_t bounds[kMaxHostChunks + 1];
+  float *d_samples;
+  uint8_t *d_payload;
+  uint64_t *d_bits, *d_boff, *d_off, *d_nout;
+  int32_t *d_status;
+  uint64_t region;   // encode: device payload bytes set aside per chunk
+  int up, kn, fin, done;   // chunks with: upload queued / kernels queued / results queued / results landed
+  unsigned boost[kMaxHostChunks];
+  uint64_t base;     // encode: payload bytes of the chunks finished so far (host side: packed densely)
+  uint64_t chunk_base[kMaxHostChunks], chunk_first[kMaxHostChunks], chunk_count[kMaxHostChunks];
+  int result;
+  bool finished;
+};
+
+struct JobEngine
+{
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  std::deque<HostJob *> queue;
+  std::thread worker;
+  bool started = false, quit = false;
+  JobRun *run[kJobSlots] = { nullptr, nullptr, nullptr, nullptr };
+  uint64_t submitted = 0, completed = 0, admitted = 0;
+  Lane lane[kJobKinds];
+  uint8_t *stage[kJobSlots] = { nullptr, nullptr, nullptr, nullptr };
+  uint64_t stage_size[kJobSlots] = { 0, 0, 0, 0 };
+  cudaEvent_t ev_in[kJobSlots][kMaxHostChunks], ev_k[kJobSlots][kMaxHostChunks], ev_out[kJobSlots][kMaxHostChunks];
+  CopyDir dir[2];   // 0: host -> device, 1: device -> host
+  uint64_t *pub = nullptr;   // mapped pinned: [slot][chunk][2] = {coder overflow flag, payload bytes}
+};
+
+// installs a lane's stream / scratch / work counter in the context for the duration of a launch sequence
+struct UseLane
+{
+  dc_ctx *c;
+  Lane *l;
+  Lane saved;
+  UseLane(dc_ctx *ctx, Lane *lane) : c(ctx), l(lane)
+  {
+    saved.stream = c->stream;
+    saved.arena = c->arena;
+    saved.arena_size = c->arena_size;
+    saved.d_work = c->d_work;
+    c->stream = l->stream;
+    c->arena = l->arena;
+    c->arena_size = l->arena_size;
+    c->d_work = l->d_work;
+  }
+  ~UseLane()
+  {
+    l->arena = c->arena;   // may have grown
+    l->arena_size = c->arena_size;
+    c->stream = saved.stream;
+    c->arena = saved.arena;
+    c->arena_size = saved.arena_size;
+    c->d_work = saved.d_work;
+  }
+};
+
+}   // extern "C"
+
+static int engine_create(dc_ctx *c)
+{
+  JobEngine *e = new (std::nothrow) JobEngine;
+  c->async_jobs = new (std::nothrow) std::vector<HostJob *>;
+  c->eng = e;
+  if (!e || !c->async_jobs)
+    return DC_ERR_MEMORY;
+  memset(e->lane, 0, sizeof(e->lane));
+  memset(e->ev_in, 0, sizeof(e->ev_in));
+  memset(e->ev_k, 0, sizeof(e->ev_k));
+  memset(e->ev_out, 0, sizeof(e->ev_out));
+  bool ok = cudaHostAlloc(&e->pub, (size_t)kJobSlots * kMaxHostChunks * 2 * sizeof(uint64_t), cudaHostAllocMapped) == cudaSuccess;
+  memset(e->dir, 0, sizeof(e->dir));
+  e->dir[0].stream = c->s_h2d;
+  e->dir[0].kind = cudaMemcpyHostToDevice;
+  e->dir[1].stream = c->s_d2h;
+  e->dir[1].kind = cudaMemcpyDeviceToHost;
+  for (int d = 0; d < 2 && ok; d++)
+    for (int i = 0; i < 8 && ok; i++)
+      ok = cudaEventCreateWithFlags(&e->dir[d].ring[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; s < kJobKinds && ok; s++)
+    ok = cudaStreamCreateWithFlags(&e->lane[s].stream, cudaStreamNonBlocking) == cudaSuccess && cudaMalloc(&e->lane[s].d_work, 256) == cudaSuccess;
+  for (int s = 0; s < kJobSlots && ok; s++)
+  {
+    for (int k = 0; k < kMaxHostChunks && ok; k++)
+      ok = cudaEventCreateWithFlags(&e->ev_in[s][k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->ev_k[s][k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->ev_out[s][k], cudaEventDisableTiming) == cudaSuccess;
+  }
+  return ok ? DC_OK : DC_ERR_LIBRARY_INIT;
+}
+
+static void engine_destroy(dc_ctx *c)
+{
+  JobEngine *e = c->eng;
+  if (e)
+  {
+    if (e->started)
+    {
+      {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->quit = true;
+      }
+      e->cv.notify_all();
+      e->worker.join();   // the worker finishes every queued job first
+    }
+    for (int s = 0; s < kJobKinds; s++)
+    {
+      if (e->lane[s].stream)
+      {
+        cudaStreamSynchronize(e->lane[s].stream);
+        cudaStreamDestroy(e->lane[s].stream);
+      }
+      if (e->lane[s].arena)
+        cudaFree(e->lane[s].arena);
+      if (e->lane[s].d_work)
+        cudaFree(e->lane[s].d_work);
+    }
+    for (int s = 0; s < kJobSlots; s++)
+    {
+      if (e->stage[s])
+        cudaFree(e->stage[s]);
+      for (int k = 0; k < kMaxHostChunks; k++)
+      {
+        if (e->ev_in[s][k])
+          cudaEventDestroy(e->ev_in[s][k]);
+        if (e->ev_k[s][k])
+          cudaEventDestroy(e->ev_k[s][k]);
+        if (e->ev_out[s][k])
+          cudaEventDestroy(e->ev_out[s][k]);
+      }
+    }
+    for (int d = 0; d < 2; d++)
+      for (int i = 0; i < 8; i++)
+        if (e->dir[d].ring[i])
+          cudaEventDestroy(e->dir[d].ring[i]);
+    if (e->pub)
+      cudaFreeHost(e->pub);
+    delete e;
+    c->eng = nullptr;
+  }
+  if (c->async_jobs)
+  {
+    for (HostJob *j : *c->async_jobs)
+      delete j;
+    delete c->async_jobs;
+    c->async_jobs = nullptr;
+  }
+}
+
 static int host_chunks(const Layout &L, uint64_t n_channels)
 {
   if (L.sample_off != nullptr || n_channels < 2)
     return 1;
-  uint64_t per = (uint64_t)sm_count() * 256;   // streams per chunk: a quarter wave of the coder kernels (1024 threads per SM)
+  uint64_t per = (uint64_t)sm_count() * (uint64_t)bac_threads_per_sm() / 2;   // streams per chunk: half a wave of the coder kernels
   if (const char *e = getenv("DC_HOST_CHUNK_STREAMS"))
     per = strtoull(e, nullptr, 10) > 0 ? strtoull(e, nullptr, 10) : per;
   uint64_t k = L.n_streams / per;
@@ -950,279 +1195,589 @@ static int host_chunks(const Layout &L, uint64_t n_channels)
 
 // Channel boundaries of the chunks, bounds[k] .. bounds[k+1]: equal shares.  (Tapering the sizes so that the chunk a
 // call cannot overlap -- the last one of an encode, the first one of a decode -- is small was tried and measured
-// slower, 35.7 / 37.0 ms against 31.7 / 32.7 ms for config 2: larger chunks in the middle cost more than the tail saves;
-// cutting only that edge chunk in two halves, nine chunks in all, measured 65.9 against 65.0 ms per encode + decode.)
+// slower in round 1: larger chunks in the middle cost more than the tail saves.)
 static void chunk_bounds(int n_chunks, uint64_t n_channels, uint64_t *bounds)
 {
   for (int k = 0; k <= n_chunks; k++)
     bounds[k] = n_channels * (uint64_t)k / (uint64_t)n_chunks;
 }
 
+static int job_stage_reserve(dc_ctx *c, int slot, uint64_t bytes)
+{
+  JobEngine *e = c->eng;
+  if (bytes <= e->stage_size[slot])
+    return DC_OK;
+  if (e->stage[slot])
+    cudaFree(e->stage[slot]);   // the slot is idle: nothing of it is in flight
+  e->stage[slot] = nullptr;
+  e->stage_size[slot] = 0;
+  const uint64_t want = round_up(bytes, 1 << 20);
+  if (cudaMalloc(&e->stage[slot], want) != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_err(c, "device staging allocation of %llu bytes failed", (unsigned long long)bytes);
+    return DC_ERR_MEMORY;
+  }
+  e->stage_size[slot] = want;
+  return DC_OK;
+}
+
+static void chunk_channels(const JobRun *r, int k, uint64_t &c0, uint64_t &c1)
+{
+  if (r->n_chunks == 1)
+  {
+    c0 = 0;
+    c1 = r->job->layout.sample_off ? 0 : r->job->layout.n_channels;
+    return;
+  }
+  c0 = r->bounds[k];
+  c1 = r->bounds[k + 1];
+}
+
+// sets up a job in its (idle) slot: geometry, device staging, the small copies that precede every chunk
+static int job_admit(dc_ctx *c, HostJob *j, JobRun *r, int slot)
+{
+  JobEngine *e = c->eng;
+  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
+  r->job = j;
+  r->slot = slot;
+  r->age = e->admitted++;
+  r->up = r->kn = r->fin = r->done = 0;
+  r->up_issued = r->out_issued = 0;
+  r->base = 0;
+  r->result = DC_OK;
+  r->finished = false;
+  int rc = make_layout(c, &j->layout, j->layout.sample_off, r->L, r->max_len, r->total);
+  if (rc != DC_OK)
+    return rc;
+  r->n = r->L.n_streams;
+  r->bpc = r->L.blocks_per_channel;
+  r->n_chunks = host_chunks(r->L, j->layout.n_channels);
+  chunk_bounds(r->n_chunks, j->layout.sample_off ? 0 : j->layout.n_channels, r->bounds);
+  for (int k = 0; k < r->n_chunks; k++)
+    r->boost[k] = 1;
+  const uint64_t n = r->n;
+  uint64_t payload_dev = 0;
+  if (j->kind == 0)
+  {
+    // every chunk gets its own region of the device payload (its start cannot depend on the sizes of the chunks before
+    // it: those are only known when their kernels have finished): the caller's capacity, or the most the chunk's
+    // samples can code to (65 SEG bits per sample at value size 32, 9/8 of that out of the coder), whichever is smaller
+    uint64_t most_channels = 0;
+    for (int k = 0; k < r->n_chunks; k++)
+    {
+      uint64_t c0, c1;
+      chunk_channels(r, k, c0, c1);
+      most_channels = std::max(most_channels, c1 - c0);
+    }
+    const uint64_t chunk_samples = r->n_chunks == 1 ? r->total : most_channels * r->L.channel_len;
+    const uint64_t chunk_streams = r->n_chunks == 1 ? n : most_channels * r->bpc;
+    const uint64_t worst = (chunk_samples * (2ull * j->params.value_size_bits + 1) * 13 / 8 + 7) / 8 + chunk_streams * 80 + 4096;
+    r->region = round_up(std::min(j->payload_size, worst) + 64, 256);
+    payload_dev = r->region * (uint64_t)r->n_chunks;
+  }
+  else
+    payload_dev = round_up(j->payload_size, 4) + 16;
+  const uint64_t need = Bump::size_of(r->total, 4) + Bump::size_of(payload_dev, 1) + 2 * Bump::size_of(n, 8) + 2 * Bump::size_of(n + 8, 8) +
+                        Bump::size_of(n, 4) + 4096;
+  if ((rc = job_stage_reserve(c, r->slot, need)) != DC_OK)
+    return rc;
+  Bump b(e->stage[r->slot]);
+  r->d_samples = b.take<float>(r->total);
+  r->d_payload = b.take<uint8_t>(payload_dev);
+  r->d_bits = b.take<uint64_t>(n);
+  r->d_nout = b.take<uint64_t>(n);
+  r->d_boff = b.take<uint64_t>(n + 8);
+  r->d_off = b.take<uint64_t>(n + 8);
+  r->d_status = b.take<int32_t>(n);
+  if (j->layout.sample_off)
+  {
+    CU_TRY(c, cudaMemcpyAsync(r->d_off, j->layout.sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+    r->L.sample_off = r->d_off;
+  }
+  if (j->kind == 1)
+  {
+    // index first (small), the payload follows chunk by chunk at its container offset
+    if (n)
+      CU_TRY(c, cudaMemcpyAsync(r->d_bits, j->bit_len_in, n * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+    CU_TRY(c, cudaMemcpyAsync(r->d_boff, j->byte_off_in, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
+  }
+  trace(c, j->kind == 0 ? "encode job admitted, chunks" : "decode job admitted, chunks", r->n_chunks);
+  return DC_OK;
+}
+
+static void chunk_streams(const JobRun *r, int k, uint64_t &s0, uint64_t &s1, uint64_t &first, uint64_t &count)
+{
+  uint64_t c0, c1;
+  chunk_channels(r, k, c0, c1);
+  if (r->n_chunks == 1)
+  {
+    s0 = 0;
+    s1 = r->n;
+    first = 0;
+    count = r->total;
+    return;
+  }
+  s0 = c0 * r->bpc;
+  s1 = c1 * r->bpc;
+  first = c0 * r->L.channel_len;
+  count = (c1 - c0) * r->L.channel_len;
+}
+
+// cuts one copy into pieces; the last piece carries `after` (a copy of 0 bytes still carries it)
+static void push_pieces(std::deque<Piece> &q, void *dst, const void *src, uint64_t bytes, cudaEvent_t after)
+{
+  uint8_t *d = static_cast<uint8_t *>(dst);
+  const uint8_t *s = static_cast<const uint8_t *>(src);
+  while (bytes > kPieceBytes)
+  {
+    q.push_back(Piece{ d, s, kPieceBytes, nullptr });
+    d += kPieceBytes;
+    s += kPieceBytes;
+    bytes -= kPieceBytes;
+  }
+  q.push_back(Piece{ d, s, bytes, after });
+}
+
+// queues the kernels of chunk k of an encode job on its lane (after the chunk's upload)
+static int encode_chunk_launch(dc_ctx *c, JobRun *r, int k)
+{
+  JobEngine *e = c->eng;
+  HostJob *j = r->job;
+  uint64_t s0, s1, first, count;
+  chunk_streams(r, k, s0, s1, first, count);
+  Layout Lk = r->L;
+  Lk.n_streams = s1 - s0;
+  UseLane use(c, &e->lane[r->slot / 2]);
+  CU_TRY(c, cudaStreamWaitEvent(c->stream, e->ev_in[r->slot][k], 0), DC_ERR_LIBRARY_CALL);
+  uint64_t *pub = e->pub + ((uint64_t)r->slot * kMaxHostChunks + k) * 2;
+  const int rc = encode_pipeline(c, FRONT_DEGA, r->d_samples + first, Lk, r->max_len, &j->params, r->d_payload + (uint64_t)k * r->region, r->region,
+                                 r->d_bits + s0, r->d_boff + s0, r->d_status + s0, nullptr, pub, r->boost[k]);
+  if (rc != DC_OK)
+    return rc;
+  CU_TRY(c, cudaEventRecord(e->ev_k[r->slot][k], c->stream), DC_ERR_LIBRARY_CALL);
+  return DC_OK;
+}
+
+// One pass over a job: queues whatever has become possible.  Returns true when something moved.
+static bool job_step(dc_ctx *c, JobRun *r)
+{
+  JobEngine *e = c->eng;
+  HostJob *j = r->job;
+  const int slot = r->slot;
+  bool moved = false;
+  auto fail = [&](int rc) {
+    // a CUDA call failed: let everything queued for this job drain, then report
+    cudaStreamSynchronize(e->lane[slot / 2].stream);
+    cudaStreamSynchronize(c->s_h2d);
+    cudaStreamSynchronize(c->s_d2h);
+    cudaGetLastError();
+    r->result = rc;
+    r->finished = true;
+    return true;
+  };
+  // 1. uploads: at most two chunks between "upload decided" and "kernels finished"
+  while (r->up < r->n_chunks && r->up < r->fin + 2)
+  {
+    const int k = r->up;
+    uint64_t s0, s1, first, count;
+    chunk_streams(r, k, s0, s1, first, count);
+    if (j->kind == 0)
+      push_pieces(r->h2d, r->d_samples + first, j->samples_in + first, count * 4, e->ev_in[slot][k]);
+    else
+    {
+      const uint64_t b0 = j->byte_off_in[s0], b1 = j->byte_off_in[s1];
+      if (b1 < b0 || b1 > j->payload_size)
+        return fail(DC_ERR_INVALID_VALUE);
+      push_pieces(r->h2d, r->d_payload + b0, j->payload_in + b0, b1 - b0, e->ev_in[slot][k]);
+    }
+    trace(c, j->kind == 0 ? "encode: upload decided, chunk" : "decode: upload decided, chunk", k);
+    r->up++;
+    moved = true;
+  }
+  // 2. kernels of every chunk whose upload has been issued (its event is recorded; stream order keeps the lane's scratch
+  //    safe from chunk to chunk)
+  while (r->kn < r->up_issued)
+  {
+    const int k = r->kn;
+    int rc;
+    if (j->kind == 0)
+      rc = encode_chunk_launch(c, r, k);
+    else
+    {
+      uint64_t s0, s1, first, count;
+      chunk_streams(r, k, s0, s1, first, count);
+      Layout Lk = r->L;
+      Lk.n_streams = s1 - s0;
+      UseLane use(c, &e->lane[slot / 2]);
+      rc = cudaStreamWaitEvent(c->stream, e->ev_in[slot][k], 0) == cudaSuccess ? DC_OK : DC_ERR_LIBRARY_CALL;
+      if (rc == DC_OK)
+        rc = decode_pipeline(c, FRONT_DEGA, r->d_payload, j->payload_size, r->d_bits + s0, r->d_boff + s0, Lk, r->max_len, &j->params,
+                             r->d_samples + first, r->d_nout + s0, r->d_status + s0);
+      if (rc == DC_OK && cudaEventRecord(e->ev_k[slot][k], c->stream) != cudaSuccess)
+        rc = DC_ERR_LIBRARY_CALL;
+    }
+    if (rc != DC_OK)
+      return fail(rc);
+    r->kn++;
+    moved = true;
+  }
+  // 3. results of the chunks whose kernels have finished, in order: only now are their copies queued (a copy that had to
+  //    wait for an event would hold up every copy queued behind it, the other job's included)
+  while (r->fin < r->kn)
+  {
+    const int k = r->fin;
+    const cudaError_t q = cudaEventQuery(e->ev_k[slot][k]);
+    if (q == cudaErrorNotReady)
+      break;
+    if (q != cudaSuccess)
+      return fail(DC_ERR_LIBRARY_CALL);
+    uint64_t s0, s1, first, count;
+    chunk_streams(r, k, s0, s1, first, count);
+    const uint64_t nk = s1 - s0;
+    if (j->kind == 0)
+    {
+      const volatile uint64_t *pub = e->pub + ((uint64_t)slot * kMaxHostChunks + k) * 2;
+      const uint64_t overflow = pub[0], tot = pub[1];
+      if (overflow != 0 && r->boost[k] < 512)
+      {
+        // a stream outgrew the coder scratch (never seen on load profiles): this chunk once more with a larger stride
+        r->boost[k] *= 8;
+        const int rc = encode_chunk_launch(c, r, k);
+        if (rc != DC_OK)
+          return fail(rc);
+        moved = true;
+        break;
+      }
+      if (overflow != 0)
+      {
+        set_err(c, "arithmetic coder output exceeded the scratch capacity");
+        r->result = DC_ERR_MEMORY;
+      }
+      const uint64_t cap_left = j->payload_size > r->base ? j->payload_size - r->base : 0;
+      if (tot > cap_left || tot > r->region)
+      {
+        set_err(c, "payload needs more than the capacity of %llu bytes", (unsigned long long)j->payload_size);
+        r->result = DC_ERR_MEMORY;
+      }
+      if (j->bit_len_out && nk)
+        push_pieces(r->d2h, j->bit_len_out + s0, r->d_bits + s0, nk * 8, nullptr);
+      if (j->byte_off_out && nk)
+        push_pieces(r->d2h, j->byte_off_out + s0, r->d_boff + s0, nk * 8, nullptr);
+      if (j->status && nk)
+        push_pieces(r->d2h, j->status + s0, r->d_status + s0, nk * 4, nullptr);
+      const bool copy_payload = r->result == DC_OK && j->payload_out && tot;
+      push_pieces(r->d2h, copy_payload ? j->payload_out + r->base : nullptr, r->d_payload + (uint64_t)k * r->region, copy_payload ? tot : 0,
+                  e->ev_out[slot][k]);
+      r->chunk_base[k] = r->base;
+      r->chunk_first[k] = s0;
+      r->chunk_count[k] = nk;
+      r->base += tot;
+    }
+    else
+    {
+      if (j->n_out && nk)
+        push_pieces(r->d2h, j->n_out + s0, r->d_nout + s0, nk * 8, nullptr);
+      if (j->status && nk)
+        push_pieces(r->d2h, j->status + s0, r->d_status + s0, nk * 4, nullptr);
+      const bool copy_samples = j->samples_out && count;
+      push_pieces(r->d2h, copy_samples ? j->samples_out + first : nullptr, r->d_samples + first, copy_samples ? count * 4 : 0, e->ev_out[slot][k]);
+    }
+    trace(c, j->kind == 0 ? "encode: kernels finished, results queued, chunk" : "decode: kernels finished, results queued, chunk", k);
+    r->fin++;
+    moved = true;
+  }
+  // 4. results landed
+  while (r->done < r->out_issued)
+  {
+    const cudaError_t q = cudaEventQuery(e->ev_out[slot][r->done]);
+    if (q == cudaErrorNotReady)
+      break;
+    if (q != cudaSuccess)
+      return fail(DC_ERR_LIBRARY_CALL);
+    r->done++;
+    moved = true;
+  }
+  if (r->done == r->n_chunks && !r->finished)
+  {
+    if (j->kind == 0)
+    {
+      if (j->byte_off_out)
+      {
+        // chunk-local offsets become container offsets (chunk 0 already is)
+        for (int k = 1; k < r->n_chunks; k++)
+          for (uint64_t i = 0; i < r->chunk_count[k]; i++)
+            j->byte_off_out[r->chunk_first[k] + i] += r->chunk_base[k];
+        j->byte_off_out[r->n] = r->base;
+      }
+      if (j->total_bytes)
+        *j->total_bytes = r->base;
+    }
+    trace(c, j->kind == 0 ? "encode job finished" : "decode job finished");
+    r->finished = true;
+    moved = true;
+  }
+  return moved;
+}
+
+// Hands pieces to one copy stream while fewer than kPiecesInFlight are in flight there.  Returns true when something moved.
+static bool pump_copies(dc_ctx *c, int d)
+{
+  JobEngine *e = c->eng;
+  CopyDir &dir = e->dir[d];
+  bool moved = false;
+  while (dir.count > 0 && cudaEventQuery(dir.ring[dir.head]) == cudaSuccess)
+  {
+    dir.head = (dir.head + 1) % 8;
+    dir.count--;
+    moved = true;
+  }
+  while (dir.count < kPiecesInFlight)
+  {
+    // whose piece: host -> device the decode's first, device -> host the kinds in turns; within a kind the older job's
+    JobRun *r = nullptr;
+    for (int t = 0; t < kJobKinds && !r; t++)
+    {
+      const int kind = d == 0 ? kJobKinds - 1 - t : (dir.turn + t) % kJobKinds;
+      for (int b = 0; b < 2; b++)
+      {
+        JobRun *cand = e->run[2 * kind + b];
+        if (cand && !cand->finished && !(d == 0 ? cand->h2d : cand->d2h).empty() && (!r || cand->age < r->age))
+          r = cand;
+      }
+    }
+    if (!r)
+      break;
+    std::deque<Piece> &q = d == 0 ? r->h2d : r->d2h;
+    const Piece p = q.front();
+    q.pop_front();
+    bool ok = p.bytes == 0 || cudaMemcpyAsync(p.dst, p.src, p.bytes, dir.kind, dir.stream) == cudaSuccess;
+    if (ok && p.after)
+    {
+      ok = cudaEventRecord(p.after, dir.stream) == cudaSuccess;
+      (d == 0 ? r->up_issued : r->out_issued)++;
+    }
+    ok = ok && cudaEventRecord(dir.ring[(dir.head + dir.count) % 8], dir.stream) == cudaSuccess;
+    dir.count++;
+    if (d == 1)
+      dir.turn = (r->slot / 2 + 1) % kJobKinds;
+    if (!ok)
+    {
+      cudaGetLastError();
+      r->result = DC_ERR_LIBRARY_CALL;
+      r->h2d.clear();
+      r->d2h.clear();
+      cudaStreamSynchronize(e->lane[r->slot / 2].stream);
+      cudaStreamSynchronize(c->s_h2d);
+      cudaStreamSynchronize(c->s_d2h);
+      r->finished = true;
+    }
+    moved = true;
+  }
+  return moved;
+}
+
+static void job_worker(dc_ctx *c)
+{
+  JobEngine *e = c->eng;
+  cudaSetDevice(c->device);
+  auto any_run = [&] {
+    for (int s = 0; s < kJobSlots; s++)
+      if (e->run[s])
+        return true;
+    return false;
+  };
+  // the slot a job of `kind` may take now, or -1: an idle kind takes its first slot; a second job joins when the one in
+  // flight has issued all its uploads
+  auto free_slot = [&](int kind) {
+    JobRun *a = e->run[2 * kind], *b = e->run[2 * kind + 1];
+    if (!a && !b)
+      return 2 * kind;
+    if (a && b)
+      return -1;
+    JobRun *busy = a ? a : b;
+    if (busy->up_issued < busy->n_chunks)
+      return -1;
+    return a ? 2 * kind + 1 : 2 * kind;
+  };
+  std::unique_lock<std::mutex> lk(e->mu);
+  for (;;)
+  {
+    e->cv.wait(lk, [&] { return e->quit || !e->queue.empty() || any_run(); });
+    if (e->quit && e->queue.empty() && !any_run())
+      return;
+    // admit queued jobs, in submission order
+    while (!e->queue.empty())
+    {
+      HostJob *j = e->queue.front();
+      const int slot = free_slot(j->kind);
+      if (slot < 0)
+        break;
+      e->queue.pop_front();
+      lk.unlock();
+      JobRun *r = new (std::nothrow) JobRun;
+      const int rc = r ? job_admit(c, j, r, slot) : DC_ERR_MEMORY;
+      lk.lock();
+      if (rc == DC_OK)
+        e->run[slot] = r;
+      else
+      {
+        delete r;
+        j->rc = rc;
+        j->done = true;
+        e->completed++;
+        e->cv_done.notify_all();
+      }
+    }
+    lk.unlock();
+    bool moved = false;
+    for (int kind = kJobKinds - 1; kind >= 0; kind--)   // the decode first: its uploads are small and what its long copy back waits for
+    {
+      JobRun *a = e->run[2 * kind], *b = e->run[2 * kind + 1];
+      if (a && b && b->age < a->age)
+        std::swap(a, b);   // the older job first: its kernels go on the lane ahead of the younger one's
+      if (a && !a->finished)
+        moved |= job_step(c, a);
+      if (b && !b->finished)
+        moved |= job_step(c, b);
+    }
+    moved |= pump_copies(c, 0);
+    moved |= pump_copies(c, 1);
+    lk.lock();
+    for (int s = 0; s < kJobSlots; s++)
+      if (e->run[s] && e->run[s]->finished)
+      {
+        HostJob *j = e->run[s]->job;
+        j->rc = e->run[s]->result;
+        j->done = true;
+        delete e->run[s];
+        e->run[s] = nullptr;
+        e->completed++;
+        e->cv_done.notify_all();
+      }
+    if (!moved && any_run())
+    {
+      lk.unlock();
+      std::this_thread::sleep_for(std::chrono::microseconds(20));   // everything queued is still running
+      lk.lock();
+    }
+  }
+}
+
+// hands a job to the worker; blocking: waits for it and returns its code
+static int job_submit(dc_ctx *c, const HostJob &proto, bool blocking)
+{
+  JobEngine *e = c->eng;
+  HostJob *j = new (std::nothrow) HostJob(proto);
+  if (!j)
+    return DC_ERR_MEMORY;
+  j->rc = DC_OK;
+  j->done = false;
+  std::unique_lock<std::mutex> lk(e->mu);
+  if (!e->started)
+  {
+    e->worker = std::thread(job_worker, c);
+    e->started = true;
+  }
+  e->queue.push_back(j);
+  e->submitted++;
+  e->cv.notify_all();
+  if (!blocking)
+  {
+    c->async_jobs->push_back(j);
+    return DC_OK;
+  }
+  e->cv_done.wait(lk, [&] { return j->done; });
+  const int rc = j->rc;
+  delete j;
+  return rc;
+}
+
+static int host_job(dc_ctx *c, bool blocking, int kind, const float *samples_in, float *samples_out, const uint8_t *payload_in, uint8_t *payload_out,
+                    uint64_t payload_size, const uint64_t *bit_len_in, const uint64_t *byte_off_in, uint64_t *bit_len_out, uint64_t *byte_off_out,
+                    const dc_layout *layout, const dc_params *params, int32_t *status, uint64_t *n_out, uint64_t *total_bytes)
+{
+  if (!c || !params_ok(params) || !layout || (kind == 1 && (!bit_len_in || !byte_off_in)))
+    return DC_ERR_INVALID_VALUE;
+  HostJob j;
+  memset(&j, 0, sizeof(j));
+  j.kind = kind;
+  j.samples_in = samples_in;
+  j.samples_out = samples_out;
+  j.payload_in = payload_in;
+  j.payload_out = payload_out;
+  j.payload_size = payload_size;
+  j.bit_len_in = bit_len_in;
+  j.byte_off_in = byte_off_in;
+  j.bit_len_out = bit_len_out;
+  j.byte_off_out = byte_off_out;
+  j.status = status;
+  j.n_out = n_out;
+  j.total_bytes = total_bytes;
+  j.layout = *layout;
+  j.params = *params;
+  return job_submit(c, j, blocking);
+}
+
+extern "C" {
+
 int dc_dega_encode_host(dc_ctx *c, const float *samples, const dc_layout *layout, const dc_params *params, uint8_t *payload,
                         uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes)
 {
-  if (!c || !params_ok(params) || !layout)
-    return DC_ERR_INVALID_VALUE;
-  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
-  Layout L;
-  uint64_t max_len, total;
-  int rc = make_layout(c, layout, layout->sample_off, L, max_len, total);
-  if (rc != DC_OK)
-    return rc;
-  const uint64_t n = L.n_streams;
-  // device payload: every chunk starts 16-byte aligned, so up to 15 bytes of padding per chunk on top of the capacity
-  const uint64_t dev_payload_cap = round_up(payload_cap, 16) + 16ull * kMaxHostChunks + 256;
-  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(dev_payload_cap, 1) + Bump::size_of(n, 8) +
-                        2 * Bump::size_of(n + 8, 8) + Bump::size_of(n, 4) + 4096;
-  if ((rc = stage_reserve(c, need)) != DC_OK)
-    return rc;
-  Bump b(c->stage);
-  float *d_samples = b.take<float>(total);
-  uint8_t *d_payload = b.take<uint8_t>(dev_payload_cap);
-  uint64_t *d_bits = b.take<uint64_t>(n);
-  uint64_t *d_boff = b.take<uint64_t>(n + 8);
-  uint64_t *d_off = b.take<uint64_t>(n + 8);
-  int32_t *d_status = b.take<int32_t>(n);
-  if (layout->sample_off)
-  {
-    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream), DC_ERR_LIBRARY_CALL);
-    L.sample_off = d_off;
-  }
-  const int n_chunks = host_chunks(L, layout->n_channels);
-  uint64_t bounds[kMaxHostChunks + 1];
-  chunk_bounds(n_chunks, layout->sample_off ? 0 : layout->n_channels, bounds);
-  const uint64_t bpc = L.blocks_per_channel;
-  // the staging block may have been read by the previous call's copy-back: order the new copies after it
-  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
-  auto chunk_range = [&](int k, uint64_t &c0, uint64_t &c1) {
-    if (n_chunks == 1)
-    {
-      c0 = 0;
-      c1 = layout->sample_off ? 0 : layout->n_channels;
-      return;
-    }
-    c0 = bounds[k];
-    c1 = bounds[k + 1];
-  };
-  auto upload = [&](int k) -> int {
-    uint64_t c0, c1;
-    chunk_range(k, c0, c1);
-    const uint64_t first = n_chunks == 1 ? 0 : c0 * L.channel_len;
-    const uint64_t count = n_chunks == 1 ? total : (c1 - c0) * L.channel_len;
-    if (count)
-      CU_TRY(c, cudaMemcpyAsync(d_samples + first, samples + first, count * 4, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
-    CU_TRY(c, cudaEventRecord(c->ev_in[k], c->s_h2d), DC_ERR_LIBRARY_CALL);
-    return DC_OK;
-  };
-  uint64_t base = 0;       // payload bytes of the chunks before this one (host side: packed densely)
-  uint64_t dev_base = 0;   // where this chunk's payload starts on the device: 16-byte aligned and past everything the chunks
-                           // before it wrote there (their copies to the host may still be in flight on s_d2h)
-  uint64_t chunk_base[kMaxHostChunks], chunk_first[kMaxHostChunks], chunk_count[kMaxHostChunks];
-  int result = DC_OK;
-  if ((rc = upload(0)) != DC_OK)
-    return rc;
-  for (int k = 0; k < n_chunks; k++)
-  {
-    if (k + 1 < n_chunks && (rc = upload(k + 1)) != DC_OK)
-      return rc;
-    uint64_t c0, c1;
-    chunk_range(k, c0, c1);
-    Layout Lk = L;
-    const uint64_t s0 = n_chunks == 1 ? 0 : c0 * bpc;
-    if (n_chunks > 1)
-      Lk.n_streams = (c1 - c0) * bpc;
-    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
-    uint64_t tot = 0;
-    const uint64_t cap_left = payload_cap > base ? payload_cap - base : 0;
-    rc = encode_pipeline(c, FRONT_DEGA, d_samples + (n_chunks == 1 ? 0 : c0 * L.channel_len), Lk, max_len, params, d_payload + dev_base,
-                         cap_left, d_bits + s0, d_boff + s0, d_status + s0, &tot);
-    if (rc != DC_OK && rc != DC_ERR_MEMORY)
-      return rc;
-    if (rc == DC_ERR_MEMORY)
-      result = rc;
-    const uint64_t nk = Lk.n_streams;
-    // encode_pipeline has synchronised the compute stream: the chunk's results are complete
-    if (bit_len && nk)
-      CU_TRY(c, cudaMemcpyAsync(bit_len + s0, d_bits + s0, nk * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    if (byte_off && nk)
-      CU_TRY(c, cudaMemcpyAsync(byte_off + s0, d_boff + s0, nk * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    if (status && nk)
-      CU_TRY(c, cudaMemcpyAsync(status + s0, d_status + s0, nk * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    if (result == DC_OK && payload && tot)
-      CU_TRY(c, cudaMemcpyAsync(payload + base, d_payload + dev_base, tot, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    chunk_base[k] = base;
-    chunk_first[k] = s0;
-    chunk_count[k] = nk;
-    base += tot;
-    dev_base = round_up(dev_base + tot, 16);
-  }
-  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
-  if (byte_off)
-  {
-    // chunk-local offsets become container offsets (chunk 0 already is)
-    for (int k = 1; k < n_chunks; k++)
-      for (uint64_t i = 0; i < chunk_count[k]; i++)
-        byte_off[chunk_first[k] + i] += chunk_base[k];
-    byte_off[n] = base;
-  }
-  if (total_bytes)
-    *total_bytes = base;
-  return result;
+  return host_job(c, true, 0, samples, nullptr, nullptr, payload, payload_cap, nullptr, nullptr, bit_len, byte_off, layout, params, status, nullptr,
+                  total_bytes);
 }
 
 int dc_dega_decode_host(dc_ctx *c, const uint8_t *payload, uint64_t payload_bytes, const uint64_t *bit_len, const uint64_t *byte_off,
                         const dc_layout *layout, const dc_params *params, float *samples, uint64_t *n_out, int32_t *status)
 {
-  if (!c || !params_ok(params) || !layout || !bit_len || !byte_off)
-    return DC_ERR_INVALID_VALUE;
-  CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
-  Layout L;
-  uint64_t max_len, total;
-  int rc = make_layout(c, layout, layout->sample_off, L, max_len, total);
-  if (rc != DC_OK)
-    return rc;
-  const uint64_t n = L.n_streams;
-  const uint64_t need = Bump::size_of(total, 4) + Bump::size_of(round_up(payload_bytes, 4) + 16, 1) + 2 * Bump::size_of(n, 8) +
-                        2 * Bump::size_of(n + 1, 8) + Bump::size_of(n, 4) + 4096;
-  if ((rc = stage_reserve(c, need)) != DC_OK)
-    return rc;
-  Bump b(c->stage);
-  float *d_samples = b.take<float>(total);
-  uint8_t *d_payload = b.take<uint8_t>(round_up(payload_bytes, 4) + 16);
-  uint64_t *d_bits = b.take<uint64_t>(n);
-  uint64_t *d_nout = b.take<uint64_t>(n);
-  uint64_t *d_boff = b.take<uint64_t>(n + 1);
-  uint64_t *d_off = b.take<uint64_t>(n + 1);
-  int32_t *d_status = b.take<int32_t>(n);
-  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
-  if (layout->sample_off)
-  {
-    CU_TRY(c, cudaMemcpyAsync(d_off, layout->sample_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
-    L.sample_off = d_off;
-  }
-  // index first (small), then the payload chunk by chunk at its container offset
-  if (n)
-    CU_TRY(c, cudaMemcpyAsync(d_bits, bit_len, n * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaMemcpyAsync(d_boff, byte_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
-  const int n_chunks = host_chunks(L, layout->n_channels);
-  uint64_t bounds[kMaxHostChunks + 1];
-  chunk_bounds(n_chunks, layout->sample_off ? 0 : layout->n_channels, bounds);
-  const uint64_t bpc = L.blocks_per_channel;
-  auto chunk_streams = [&](int k, uint64_t &s0, uint64_t &s1, uint64_t &c0, uint64_t &c1) {
-    if (n_chunks == 1)
-    {
-      s0 = 0;
-      s1 = n;
-      c0 = 0;
-      c1 = layout->n_channels;
-      return;
-    }
-    c0 = bounds[k];
-    c1 = bounds[k + 1];
-    s0 = c0 * bpc;
-    s1 = c1 * bpc;
-  };
-  auto upload = [&](int k) -> int {
-    uint64_t s0, s1, c0, c1;
-    chunk_streams(k, s0, s1, c0, c1);
-    const uint64_t b0 = byte_off[s0], b1 = byte_off[s1];
-    if (b1 < b0 || b1 > payload_bytes)
-      return DC_ERR_INVALID_VALUE;
-    if (b1 > b0)
-      CU_TRY(c, cudaMemcpyAsync(d_payload + b0, payload + b0, b1 - b0, cudaMemcpyHostToDevice, c->s_h2d), DC_ERR_LIBRARY_CALL);
-    CU_TRY(c, cudaEventRecord(c->ev_in[k], c->s_h2d), DC_ERR_LIBRARY_CALL);
-    return DC_OK;
-  };
-  if ((rc = upload(0)) != DC_OK)
-    return rc;
-  for (int k = 0; k < n_chunks; k++)
-  {
-    if (k + 1 < n_chunks && (rc = upload(k + 1)) != DC_OK)
-      return rc;
-    uint64_t s0, s1, c0, c1;
-    chunk_streams(k, s0, s1, c0, c1);
-    Layout Lk = L;
-    if (n_chunks > 1)
-      Lk.n_streams = s1 - s0;
-    const uint64_t first = n_chunks == 1 ? 0 : c0 * L.channel_len;
-    const uint64_t count = n_chunks == 1 ? total : (c1 - c0) * L.channel_len;
-    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[k], 0), DC_ERR_LIBRARY_CALL);
-    rc = decode_pipeline(c, FRONT_DEGA, d_payload, payload_bytes, d_bits + s0, d_boff + s0, Lk, max_len, params, d_samples + first, d_nout + s0,
-                         d_status + s0);
-    if (rc != DC_OK)
-      return rc;
-    CU_TRY(c, cudaEventRecord(c->ev_out[k], c->stream), DC_ERR_LIBRARY_CALL);
-    CU_TRY(c, cudaStreamWaitEvent(c->s_d2h, c->ev_out[k], 0), DC_ERR_LIBRARY_CALL);
-    if (samples && count)
-      CU_TRY(c, cudaMemcpyAsync(samples + first, d_samples + first, count * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    if (n_out && s1 > s0)
-      CU_TRY(c, cudaMemcpyAsync(n_out + s0, d_nout + s0, (s1 - s0) * 8, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-    if (status && s1 > s0)
-      CU_TRY(c, cudaMemcpyAsync(status + s0, d_status + s0, (s1 - s0) * 4, cudaMemcpyDeviceToHost, c->s_d2h), DC_ERR_LIBRARY_CALL);
-  }
-  CU_TRY(c, cudaStreamSynchronize(c->s_d2h), DC_ERR_LIBRARY_CALL);
-  CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
-  const cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess)
-  {
-    set_err(c, "kernel execution failed: %s", cudaGetErrorString(e));
-    return DC_ERR_LIBRARY_CALL;
-  }
-  return DC_OK;
+  return host_job(c, true, 1, nullptr, samples, payload, nullptr, payload_bytes, bit_len, byte_off, nullptr, nullptr, layout, params, status, n_out,
+                  nullptr);
 }
 
-// ---- asynchronous forms of the two host-buffer calls --------------------------------------------------------
-// The call runs on a worker thread owned by the context and dc_wait() joins it.  A context has its own streams, copy
-// engines' queues and staging memory, so an encode on one context (mostly host -> device traffic) and a decode on
-// another (mostly device -> host) use both directions of the PCIe link at once; one context alone is half duplex.
-static int start_worker(dc_ctx *c, std::thread *t)
-{
-  if (!t)
-    return DC_ERR_MEMORY;
-  c->worker = t;
-  return DC_OK;
-}
-
+// Asynchronous forms: the job is queued and the call returns; dc_wait() blocks until every queued job has finished.
 int dc_dega_encode_host_async(dc_ctx *c, const float *samples, const dc_layout *layout, const dc_params *params, uint8_t *payload,
                               uint64_t payload_cap, uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes)
 {
-  if (!c || !params_ok(params) || !layout)
-    return DC_ERR_INVALID_VALUE;
-  if (c->worker)
-    return DC_ERR_INVALID_MODE;   // one call in flight per context
-  const dc_layout lay = *layout;
-  const dc_params par = *params;
-  c->worker_rc = DC_OK;
-  return start_worker(c, new (std::nothrow) std::thread([=]() {
-                        c->worker_rc = dc_dega_encode_host(c, samples, &lay, &par, payload, payload_cap, bit_len, byte_off, status, total_bytes);
-                      }));
+  return host_job(c, false, 0, samples, nullptr, nullptr, payload, payload_cap, nullptr, nullptr, bit_len, byte_off, layout, params, status, nullptr,
+                  total_bytes);
 }
 
 int dc_dega_decode_host_async(dc_ctx *c, const uint8_t *payload, uint64_t payload_bytes, const uint64_t *bit_len, const uint64_t *byte_off,
                               const dc_layout *layout, const dc_params *params, float *samples, uint64_t *n_out, int32_t *status)
 {
-  if (!c || !params_ok(params) || !layout || !bit_len || !byte_off)
+  return host_job(c, false, 1, nullptr, samples, payload, nullptr, payload_bytes, bit_len, byte_off, nullptr, nullptr, layout, params, status, n_out,
+                  nullptr);
+}
+
+int dc_wait_next(dc_ctx *c)
+{
+  if (!c)
     return DC_ERR_INVALID_VALUE;
-  if (c->worker)
-    return DC_ERR_INVALID_MODE;
-  const dc_layout lay = *layout;
-  const dc_params par = *params;
-  c->worker_rc = DC_OK;
-  return start_worker(c, new (std::nothrow) std::thread([=]() {
-                        c->worker_rc = dc_dega_decode_host(c, payload, payload_bytes, bit_len, byte_off, &lay, &par, samples, n_out, status);
-                      }));
+  if (c->async_jobs->empty())
+    return DC_OK;
+  JobEngine *e = c->eng;
+  HostJob *j = c->async_jobs->front();
+  c->async_jobs->erase(c->async_jobs->begin());
+  std::unique_lock<std::mutex> lk(e->mu);
+  e->cv_done.wait(lk, [&] { return j->done; });
+  const int rc = j->rc;
+  delete j;
+  return rc;
 }
 
 int dc_wait(dc_ctx *c)
 {
   if (!c)
     return DC_ERR_INVALID_VALUE;
-  if (!c->worker)
-    return DC_OK;
-  c->worker->join();
-  delete c->worker;
-  c->worker = nullptr;
-  return c->worker_rc;
+  int rc = DC_OK;
+  while (!c->async_jobs->empty())
+  {
+    const int r = dc_wait_next(c);
+    if (rc == DC_OK)
+      rc = r;   // the first failure, in submission order
+  }
+  return rc;
 }
 
 // ---- LZMH ---------------------------------------------------------------------------------------------------

@@ -36,8 +36,9 @@ __device__ __forceinline__ void warp_tasks(unsigned int *work, uint64_t n_stream
     if (w >= n_tasks)
       break;
     const uint64_t s = (uint64_t)w * 32 + lane;
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, s < n_streams);   // the lanes that run a stream in this task
     if (s < n_streams)
-      body(s);
+      body(s, mask);
     __syncwarp();
   }
 }
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(128) front_kernel(const FrontArgs a)
 // spills), 1.02 at 10, 1.12 at 12, 1.30 at 16 (spills): the kernel is issue bound, extra warps only add pressure
 __global__ void __launch_bounds__(128, FRONT_MIN_CTAS) front_dega_kernel(const FrontArgs a)
 {
-  warp_tasks(a.work, a.lay.n_streams, [&](uint64_t s) { front_dega_body(a, s); });
+  warp_tasks(a.work, a.lay.n_streams, [&](uint64_t s, unsigned) { front_dega_body(a, s); });
 }
 
 void launch_front(const FrontArgs &a, cudaStream_t st)
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(128, BACK_MIN_CTAS) back_dega_kernel(const Bac
 {
   __shared__ float stage[128 * kBackStage];   // decoded samples per thread, leaving as 128-bit stores of whole sectors
   float *mine = stage + threadIdx.x * kBackStage;
-  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { back_dega_body<MODE>(a, s, mine); });
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s, unsigned) { back_dega_body<MODE>(a, s, mine); });
 }
 
 void launch_back(const BackArgs &a, cudaStream_t st)
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(kBacThreads, 1) bac_encode_kernel(const BacArg
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { bac_encode_body<ADAPTIVE>(a, s, tab); });
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s, unsigned mask) { bac_encode_body<ADAPTIVE>(a, s, tab, mask); });
 }
 
 template <bool ADAPTIVE>
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kBacThreads, 1) bac_decode_kernel(const BacArg
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DivEntry *tab = reinterpret_cast<DivEntry *>(smem_raw);
   load_div_table(tab, a.div_table);
-  warp_tasks(a.work, a.n_streams, [&](uint64_t s) { bac_decode_body<ADAPTIVE>(a, s, tab); });
+  warp_tasks(a.work, a.n_streams, [&](uint64_t s, unsigned mask) { bac_decode_body<ADAPTIVE>(a, s, tab, mask); });
 }
 
 template <typename K>
@@ -707,6 +708,21 @@ void launch_validate_index(const uint64_t *bit_len, const uint64_t *byte_off, ui
   if (n == 0)
     return;
   validate_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bit_len, byte_off, n, payload_bytes, status);
+  g_launches++;
+}
+
+// Hands two device scalars (the coder's overflow flag, the payload total) to the host through mapped pinned memory: no
+// copy-engine operation, so the read cannot queue behind the bulk copies of another job (see the job engine in api.cu).
+__global__ void publish_kernel(const uint64_t *flag, const uint64_t *total, volatile uint64_t *pub)
+{
+  pub[0] = *flag;
+  pub[1] = *total;
+  __threadfence_system();
+}
+
+void launch_publish(const uint64_t *d_flag, const uint64_t *d_total, uint64_t *pub, cudaStream_t st)
+{
+  publish_kernel<<<1, 1, 0, st>>>(d_flag, d_total, pub);
   g_launches++;
 }
 

@@ -147,6 +147,9 @@ void launch_gather(const uint8_t *scratch, uint64_t stride_bytes, const uint64_t
 // marks streams whose byte range [byte_off[s], + ceil(bit_len[s] / 8)) leaves the payload with ERROR_INVALID_FORMAT
 void launch_validate_index(const uint64_t *bit_len, const uint64_t *byte_off, uint64_t n, uint64_t payload_bytes, int32_t *status, cudaStream_t st);
 
+// writes {*d_flag, *d_total} to pub[0..1] (mapped pinned host memory)
+void launch_publish(const uint64_t *d_flag, const uint64_t *d_total, uint64_t *pub, cudaStream_t st);
+
 // ---- aggregate (granularity reduction): out[c][g] = sum of in[c][g*k .. g*k+k), strictly sequential float32 adds
 void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len, uint32_t num_values, float *out, cudaStream_t st);
 

@@ -139,13 +139,16 @@ int dc_dega_decode_host(dc_ctx *ctx, const uint8_t *payload, uint64_t payload_by
                         const dc_layout *layout, const dc_params *params,
                         float *samples, uint64_t *n_out, int32_t *status);
 
-/* Asynchronous forms of the two calls above: same arguments and results, but the call returns at once and the work
-   (copies in, kernels, copies out) proceeds on a worker thread owned by the context; dc_wait() blocks until it is
-   done and returns its code.  One call in flight per context (a second one returns DC_ERR_INVALID_MODE); every buffer
-   and *total_bytes must stay valid until dc_wait() returns; layout and params are copied.  The reason to use them: one
-   call keeps one direction of the PCIe link busy (an encode is mostly host -> device, a decode mostly device ->
-   host), so an encode on one context running next to a decode on another uses the link full duplex.  The reference
-   has no analogue (one DCCLI process per stream, DCCLI/src/cli.c:407-473); its unit of overlap is the process. */
+/* Asynchronous forms of the two calls above: same arguments and results, but the call only queues the job and
+   returns; dc_wait() blocks until every job queued on the context has finished and returns the first non-zero code
+   among them, in submission order.  A context runs at most one encode and one decode at a time (further jobs wait
+   their turn, in order); every buffer and *total_bytes must stay valid until dc_wait() returns (layout and params are
+   copied), and no other call may be made on the context meanwhile.  The reason to use them: an encode is mostly host
+   -> device traffic and a decode mostly device -> host, so an encode queued next to a decode keeps both directions of
+   the PCIe link busy, where one call after the other uses one direction at a time.  The library issues the copies of
+   the two jobs itself, interleaved on one stream per direction (csrc/api.cu, "the job engine"); two contexts with
+   their own copy streams do NOT overlap on this hardware.  The reference has no analogue (one DCCLI process per
+   stream, DCCLI/src/cli.c:407-473); its unit of overlap is the process. */
 int dc_dega_encode_host_async(dc_ctx *ctx, const float *samples, const dc_layout *layout, const dc_params *params,
                               uint8_t *payload, uint64_t payload_cap,
                               uint64_t *bit_len, uint64_t *byte_off, int32_t *status, uint64_t *total_bytes);
@@ -154,6 +157,10 @@ int dc_dega_decode_host_async(dc_ctx *ctx, const uint8_t *payload, uint64_t payl
                               const dc_layout *layout, const dc_params *params,
                               float *samples, uint64_t *n_out, int32_t *status);
 int dc_wait(dc_ctx *ctx);
+/* Waits for the OLDEST asynchronous job not yet collected and returns its code (DC_OK when there is none).  For
+   streaming use: keep queueing jobs and collect them in submission order, so that the copies and kernels of the next
+   job start while the results of this one are being consumed. */
+int dc_wait_next(dc_ctx *ctx);
 
 /* ---- batch face: A-XDR = normalize only ---------------------------------------------------- */
 /* `encode normalize` (normalize.c:9-27) for every stream: stream s becomes len(s) * value_size_bits

@@ -508,35 +508,45 @@ def test_decoders_reject_an_index_that_leaves_the_payload(ctx, oracle):
     assert out[:2000].cpu().numpy().tobytes() == data[:2000].cpu().numpy().tobytes()
 
 
-def test_async_host_calls_on_two_contexts(ctx, oracle):
-    """dc_dega_encode_host_async / dc_dega_decode_host_async / dc_wait: same results as the blocking calls, an encode
-    on one context running next to a decode on another, a second call on a busy context refused."""
-    from data_compressor_b200 import Context, synth
+def test_async_host_calls_overlap_an_encode_and_a_decode(ctx, oracle):
+    """dc_dega_encode_host_async / dc_dega_decode_host_async / dc_wait: an encode and a decode in flight on ONE context
+    (the job engine interleaves their chunks), jobs of the same kind queue up in order; results equal the blocking calls'."""
+    from data_compressor_b200 import synth
     nc, cl, bl = 300, 3000, 250
     x = synth.redd_like(nc, cl, device="cpu", seed=31).numpy()
     x2 = synth.redd_like(nc, cl, device="cpu", seed=32).numpy()
-    ctx2 = Context(0)
-    try:
-        ref_enc = [np.array(a, copy=True) for a in ctx.dega_encode_host(x, block_len=bl)]
-        ref2 = [np.array(a, copy=True) for a in ctx.dega_encode_host(x2, block_len=bl)]
+    ref_enc = [np.array(a, copy=True) for a in ctx.dega_encode_host(x, block_len=bl)]
+    ref2 = [np.array(a, copy=True) for a in ctx.dega_encode_host(x2, block_len=bl)]
+    for rep in range(3):
         pe = ctx.dega_encode_host(x2, block_len=bl, wait=False, slot=1)
-        par, lay = ctx._params(32, 100.0, True), ctx._layout(nc, cl, bl)
-        import ctypes as C
-        rc = ctx.lib.dc_dega_encode_host_async(ctx.h, x.ctypes.data, C.byref(lay), C.byref(par), None, 0, None, None, None, None)
-        assert rc == -4                                                   # one call in flight per context
-        pd = ctx2.dega_decode_host(ref_enc[0], ref_enc[1], ref_enc[2], nc, cl, bl, wait=False)
-        got2 = pe.wait()
+        pd = ctx.dega_decode_host(ref_enc[0], ref_enc[1], ref_enc[2], nc, cl, bl, wait=False)
+        got2 = pe.wait()          # dc_wait: both jobs are finished after it
         y, n_out, st = pd.wait()
         assert np.array_equal(y.view(np.uint32), x.view(np.uint32)) and not st.any() and (n_out == bl).all()
         for a, b in zip(got2, ref2):
             assert np.array_equal(a, b)
-        s = 1234
-        c, b = divmod(s, cl // bl)
-        want = oracle.dega_encode(x2[c, b * bl:(b + 1) * bl])[1]
-        assert got2[0][int(got2[2][s]):int(got2[2][s]) + len(want)].tobytes() == want
-        assert ctx.lib.dc_wait(ctx.h) == 0                                # nothing in flight: a no-op
-    finally:
-        ctx2.close()
+    s = 1234
+    c, b = divmod(s, cl // bl)
+    want = oracle.dega_encode(x2[c, b * bl:(b + 1) * bl])[1]
+    assert got2[0][int(got2[2][s]):int(got2[2][s]) + len(want)].tobytes() == want
+    # two encodes queued behind each other on the same context: they run in order, each into its own buffers
+    p1 = ctx.dega_encode_host(x, block_len=bl, wait=False, slot=0)
+    p2 = ctx.dega_encode_host(x2, block_len=bl, wait=False, slot=1)
+    g1, g2 = p1.wait(), p2.wait()
+    for a, b in zip(g1, ref_enc):
+        assert np.array_equal(a, b)
+    for a, b in zip(g2, ref2):
+        assert np.array_equal(a, b)
+    assert ctx.lib.dc_wait(ctx.h) == 0                                # nothing in flight: a no-op
+    # an asynchronous job that fails reports through dc_wait (payload capacity far too small)
+    import ctypes as C
+    par, lay = ctx._params(32, 100.0, True), ctx._layout(nc, cl, bl)
+    n = ctx.n_streams(nc, cl, bl)
+    small = np.zeros(64, dtype=np.uint8)
+    blen, boff, stat, tot = np.zeros(n, np.uint64), np.zeros(n + 1, np.uint64), np.zeros(n, np.int32), C.c_uint64(0)
+    assert ctx.lib.dc_dega_encode_host_async(ctx.h, x.ctypes.data, C.byref(lay), C.byref(par), small.ctypes.data, small.size, blen.ctypes.data,
+                                             boff.ctypes.data, stat.ctypes.data, C.byref(tot)) == 0
+    assert ctx.lib.dc_wait(ctx.h) == -6 and tot.value == ref_enc[0].size
 
 
 # ---- aggregate (granularity reduction, SURVEY 8f-2) ------------------------------------------------------------
