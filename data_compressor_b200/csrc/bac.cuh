@@ -30,7 +30,8 @@
 //             index 2: lo += B, rng = A - B                      B = floor(rng / cum[0])
 //             EOF    : rng = B                                    (bac.c:109-111 with the cum[] above)
 //   division  total <= 16383 and rng * cum[1] <= 2^30, so floor(x / total) == umulhi(x, m) >> s with a
-//             precomputed round-up reciprocal (m, s) per divisor (kernels.h: DivEntry); exact, no correction step.
+//             precomputed round-up reciprocal m per divisor (kernels.h: DivEntry) and s = ceil(log2 total) - 2; exact, no
+//             correction step.  rng / total itself (rng <= 2^16) needs no shift: umulhi(rng, mb), mb = ceil(2^32 / total).
 //   end       EOF symbol, then FinishEncoding (bac.c:141-145): one more pending bit, then the bit
 //             (lo < 0x4000 ? 0 : 1) followed by the inverted run -- in the exact view: add 0x4000 to the window
 //             (with carry) and shift two more bits out.
@@ -57,8 +58,12 @@ __device__ __forceinline__ uint32_t clz_nz(uint32_t a)
 }
 #endif
 
-// floor(x / d) for x <= 2^30 with the table entry of d
-__device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e) { return __umulhi(x, e.m) >> e.s; }
+// shift that goes with DivEntry::m of divisor d >= 3: ceil(log2 d) - 2
+__device__ __forceinline__ uint32_t div_shift(uint32_t d) { return 30u - clz_nz(d - 1u); }
+// floor(x / d) for x < 2^30 with the table entry of d and sh = div_shift(d)
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, const DivEntry e, uint32_t sh) { return __umulhi(x, e.m) >> sh; }
+// floor(x / d) for x <= 2^16
+__device__ __forceinline__ uint32_t div_small(uint32_t x, const DivEntry e) { return __umulhi(x, e.mb); }
 
 struct BacModel
 {
@@ -113,7 +118,10 @@ struct BacModel
 // Out: dlo = what is added to lo, base - dlo = the new range.
 // SWAP = false is for groups in which the symbols cannot trade places (freq[1] - freq[2] >= group length at the
 // start of the group): the update is then a single predicated increment of f_oth, and the caller adds the number
-// of index-1 symbols to f_top after the group.
+// of index-1 symbols to f_top after the group.  That form (bac_take_*) also avoids the two selects: a select, like a
+// shift or a logic operation, takes the scheduler two cycles on this part while an add, a compare or a predicated
+// move takes one (profiles/r2_ubench_pipes.txt), so it computes r1 = rng - A, then on the rarer symbol overwrites it
+// with A - B and moves B over A.
 template <bool ADAPTIVE, bool SWAP>
 __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_t A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &dlo,
                                              uint32_t &base)
@@ -169,6 +177,87 @@ __device__ __forceinline__ void bac_pick_enc(uint32_t &x, uint32_t mask, uint32_
         "}"
         : "=&r"(dlo), "=&r"(base)
         : "r"(x), "r"(mask), "r"(A), "r"(B), "r"(rng));
+#endif
+}
+
+// In: A, B, rng; the symbol sits at index 2 when (x & mask) != 0.  Out: A = what is added to lo, r1 = the new range.
+template <bool ADAPTIVE>
+__device__ __forceinline__ void bac_take_enc(uint32_t x, uint32_t mask, uint32_t &A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &r1)
+{
+#ifdef DC_HOST_SIM
+  const bool nontop = (x & mask) != 0;
+  r1 = nontop ? A - B : rng - A;
+  if (nontop)
+    A = B;
+  if (ADAPTIVE && nontop)
+    m.f_oth++;
+#else
+  if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %3, %4;\n\t"
+        "setp.ne.u32 pn, t, 0;\n\t"
+        "sub.u32 %0, %6, %1;\n\t"
+        "@pn sub.u32 %0, %1, %5;\n\t"
+        "@pn mov.u32 %1, %5;\n\t"
+        "@pn add.u32 %2, %2, 1;\n\t"
+        "}"
+        : "=&r"(r1), "+r"(A), "+r"(m.f_oth)
+        : "r"(x), "r"(mask), "r"(B), "r"(rng));
+  else
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 pn, t, 0;\n\t"
+        "sub.u32 %0, %5, %1;\n\t"
+        "@pn sub.u32 %0, %1, %4;\n\t"
+        "@pn mov.u32 %1, %4;\n\t"
+        "}"
+        : "=&r"(r1), "+r"(A)
+        : "r"(x), "r"(mask), "r"(B), "r"(rng));
+#endif
+}
+
+// Decoder: the symbol sits at index 2 when o < A; `nontop` collects those positions.
+template <bool ADAPTIVE>
+__device__ __forceinline__ void bac_take_dec(uint32_t o, uint32_t bit, uint32_t &A, uint32_t B, uint32_t rng, BacModel &m, uint32_t &nontop, uint32_t &r1)
+{
+#ifdef DC_HOST_SIM
+  const bool is_nontop = o < A;
+  r1 = is_nontop ? A - B : rng - A;
+  if (is_nontop)
+  {
+    A = B;
+    nontop |= bit;
+    if (ADAPTIVE)
+      m.f_oth++;
+  }
+#else
+  if (ADAPTIVE)
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        "setp.lt.u32 pn, %4, %1;\n\t"
+        "sub.u32 %0, %7, %1;\n\t"
+        "@pn sub.u32 %0, %1, %6;\n\t"
+        "@pn mov.u32 %1, %6;\n\t"
+        "@pn or.b32 %3, %3, %5;\n\t"
+        "@pn add.u32 %2, %2, 1;\n\t"
+        "}"
+        : "=&r"(r1), "+r"(A), "+r"(m.f_oth), "+r"(nontop)
+        : "r"(o), "r"(bit), "r"(B), "r"(rng));
+  else
+    asm("{\n\t"
+        ".reg .pred pn;\n\t"
+        "setp.lt.u32 pn, %3, %1;\n\t"
+        "sub.u32 %0, %6, %1;\n\t"
+        "@pn sub.u32 %0, %1, %5;\n\t"
+        "@pn mov.u32 %1, %5;\n\t"
+        "@pn or.b32 %2, %2, %4;\n\t"
+        "}"
+        : "=&r"(r1), "+r"(A), "+r"(nontop)
+        : "r"(o), "r"(bit), "r"(B), "r"(rng));
 #endif
 }
 
@@ -382,10 +471,10 @@ struct BacEncoder
   }
 
   // EncodeSymbol for a data bit (bac.c:107-111); c1m1 = cum[1] - 1
-  __device__ __forceinline__ void encode_bit(bool is_top, uint32_t c1m1, const DivEntry e, CarryWriter &w)
+  __device__ __forceinline__ void encode_bit(bool is_top, uint32_t c1m1, const DivEntry e, uint32_t sh, CarryWriter &w)
   {
-    const uint32_t A = div_magic(rng * c1m1 + rng, e);
-    const uint32_t B = div_magic(rng, e);
+    const uint32_t A = div_magic(rng * c1m1 + rng, e, sh);
+    const uint32_t B = div_small(rng, e);
     const uint32_t dlo = is_top ? A : B;
     const uint32_t base = is_top ? rng : A;
     narrow(dlo, base - dlo, w);
@@ -394,7 +483,7 @@ struct BacEncoder
   // EOF symbol (bac.c:163) followed by FinishEncoding (bac.c:141-145)
   __device__ __forceinline__ void finish(const DivEntry e, CarryWriter &w)
   {
-    narrow(0, div_magic(rng, e), w);
+    narrow(0, div_small(rng, e), w);
     drain(w);
     const uint64_t x = (((uint64_t)a0 << 32) | LO) + 0x40000000ull;
     a0 = (uint32_t)(x >> 32);

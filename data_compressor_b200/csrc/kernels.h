@@ -35,29 +35,37 @@ __host__ __device__ inline void stream_extent(const Layout &L, uint64_t s, uint6
   }
 }
 
-// Division table for the arithmetic coder: for 3 <= d < 16384, entry d = {m, s} with
-//   floor(x / d) == umulhi(x, m) >> s          for every x < 2^30
-// (exact Granlund-Montgomery round-up reciprocal: l = ceil(log2 d), m = ceil(2^(30+l) / d) < 2^31, s = l - 2).
+// Division table for the arithmetic coder: for 3 <= d < 16384, entry d = {m, mb} with
+//   floor(x / d) == umulhi(x, m) >> div_shift(d)     for every x < 2^30      (rng * cum[1], bac.c:110-111)
+//   floor(x / d) == umulhi(x, mb)                     for every x <= 2^16     (rng itself: no shift needed)
+// Exact round-up reciprocals (Granlund-Montgomery): l = ceil(log2 d), m = ceil(2^(30+l) / d) < 2^31, shift l - 2;
+// mb = ceil(2^32 / d): its error term x * (mb * d - 2^32) stays below 2^16 * 2^14 < 2^32.  The shift depends on d through
+// l only, i.e. it changes where d passes a power of two, so the unrolled symbol groups keep it in a register.
 // Entries 0..2 are unused (the coder's total frequency is at least 3).
 struct DivEntry
 {
   uint32_t m;
-  uint32_t s;
+  uint32_t mb;
 };
 static const int kDivTableEntries = 16384;
+inline uint32_t div_shift_host(uint32_t d)   // l - 2
+{
+  uint32_t l = 0;
+  while ((1u << l) < d)
+    l++;
+  return l - 2;
+}
 inline void build_div_table(DivEntry *t)
 {
   for (uint32_t d = 0; d < (uint32_t)kDivTableEntries; d++)
   {
     t[d].m = 0;
-    t[d].s = 0;
+    t[d].mb = 0;
     if (d < 3)
       continue;
-    uint32_t l = 0;
-    while ((1u << l) < d)
-      l++;
+    const uint32_t l = div_shift_host(d) + 2;
     t[d].m = (uint32_t)((((uint64_t)1 << (30 + l)) + d - 1) / d);
-    t[d].s = l - 2;
+    t[d].mb = (uint32_t)((((uint64_t)1 << 32) + d - 1) / d);
   }
 }
 

@@ -99,6 +99,55 @@ BODY(k_flo_lop, asm volatile("bfind.shiftamt.u32 %0, %4; lop3.b32 %1, %1, %5, %8
                          "lop3.b32 %4, %4, %0, %8, 0x96; lop3.b32 %5, %5, %1, %8, 0xe8; lop3.b32 %6, %6, %2, %8, 0xe8; lop3.b32 %7, %7, %3, %8, 0xe8;"
                          : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h) : "r"(k));)
 
+
+// ---- round 2: which instructions issue at full rate?  (candidates for replacing the half-rate LOP3 / SHF / SEL / IMAD)
+BODY(k_fsel, { float fa = __uint_as_float(a), fb = __uint_as_float(b), fc = __uint_as_float(c), fd = __uint_as_float(d), fe = __uint_as_float(e), ff = __uint_as_float(f), fg = __uint_as_float(g), fh = __uint_as_float(h);
+  asm volatile("{ .reg .pred p; setp.lt.u32 p, %8, 77; selp.f32 %0, %1, %4, p; selp.f32 %1, %2, %5, p; selp.f32 %2, %3, %6, p; selp.f32 %3, %4, %7, p;"
+               "selp.f32 %4, %5, %0, p; selp.f32 %5, %6, %1, p; selp.f32 %6, %7, %2, p; selp.f32 %7, %0, %3, p; }"
+               : "+f"(fa), "+f"(fb), "+f"(fc), "+f"(fd), "+f"(fe), "+f"(ff), "+f"(fg), "+f"(fh) : "r"(k + i));
+  a = __float_as_uint(fa); b = __float_as_uint(fb); c = __float_as_uint(fc); d = __float_as_uint(fd); e = __float_as_uint(fe); f = __float_as_uint(ff); g = __float_as_uint(fg); h = __float_as_uint(fh); })
+BODY(k_selp, asm volatile("{ .reg .pred p; setp.lt.u32 p, %8, 77; selp.u32 %0, %1, %4, p; selp.u32 %1, %2, %5, p; selp.u32 %2, %3, %6, p; selp.u32 %3, %4, %7, p;"
+                          "selp.u32 %4, %5, %0, p; selp.u32 %5, %6, %1, p; selp.u32 %6, %7, %2, p; selp.u32 %7, %0, %3, p; }"
+                          : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h) : "r"(k + i));)
+BODY(k_fadd, { float fa = __uint_as_float(a), fb = __uint_as_float(b), fc = __uint_as_float(c), fd = __uint_as_float(d), fe = __uint_as_float(e), ff = __uint_as_float(f), fg = __uint_as_float(g), fh = __uint_as_float(h);
+  asm volatile("add.rn.f32 %0, %0, %4; add.rn.f32 %1, %1, %5; add.rn.f32 %2, %2, %6; add.rn.f32 %3, %3, %7;"
+               "mul.rn.f32 %4, %4, %0; mul.rn.f32 %5, %5, %1; mul.rn.f32 %6, %6, %2; mul.rn.f32 %7, %7, %3;"
+               : "+f"(fa), "+f"(fb), "+f"(fc), "+f"(fd), "+f"(fe), "+f"(ff), "+f"(fg), "+f"(fh));
+  a = __float_as_uint(fa); b = __float_as_uint(fb); c = __float_as_uint(fc); d = __float_as_uint(fd); e = __float_as_uint(fe); f = __float_as_uint(ff); g = __float_as_uint(fg); h = __float_as_uint(fh); })
+BODY(k_lea, asm volatile("{ .reg .u32 t; shl.b32 t, %4, 16; add.u32 %0, %0, t; shl.b32 t, %5, 16; add.u32 %1, %1, t; shl.b32 t, %6, 16; add.u32 %2, %2, t; shl.b32 t, %7, 16; add.u32 %3, %3, t;"
+                         "shl.b32 t, %0, 16; add.u32 %4, %4, t; shl.b32 t, %1, 16; add.u32 %5, %5, t; shl.b32 t, %2, 16; add.u32 %6, %6, t; shl.b32 t, %3, 16; add.u32 %7, %7, t; }"
+                         : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h));)
+BODY(k_prmt, asm volatile("prmt.b32 %0, %0, %4, %8; prmt.b32 %1, %1, %5, %8; prmt.b32 %2, %2, %6, %8; prmt.b32 %3, %3, %7, %8;"
+                          "prmt.b32 %4, %4, %0, %8; prmt.b32 %5, %5, %1, %8; prmt.b32 %6, %6, %2, %8; prmt.b32 %7, %7, %3, %8;"
+                          : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h) : "r"(k & 0x7777));)
+BODY(k_add_pred, asm volatile("{ .reg .pred p; setp.lt.u32 p, %8, 77; @p add.u32 %0, %0, %4; @p add.u32 %1, %1, %5; @p add.u32 %2, %2, %6; @p add.u32 %3, %3, %7;"
+                              "@!p add.u32 %4, %4, %0; @!p add.u32 %5, %5, %1; @!p add.u32 %6, %6, %2; @!p add.u32 %7, %7, %3; }"
+                              : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h) : "r"(k + i));)
+BODY(k_setp, asm volatile("{ .reg .pred p0, p1, p2, p3; setp.lt.u32 p0, %0, %4; setp.lt.u32 p1, %1, %5; setp.lt.u32 p2, %2, %6; setp.lt.u32 p3, %3, %7;"
+                          "@p0 add.u32 %4, %4, %0; @p1 add.u32 %5, %5, %1; @p2 add.u32 %6, %6, %2; @p3 add.u32 %7, %7, %3; }"
+                          : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h));)
+BODY(k_iadd3x, asm volatile("{ .reg .u32 t; add.cc.u32 %0, %0, %4; addc.u32 %1, %1, %5; add.cc.u32 %2, %2, %6; addc.u32 %3, %3, %7;"
+                            "add.cc.u32 %4, %4, %1; addc.u32 %5, %5, %0; add.cc.u32 %6, %6, %3; addc.u32 %7, %7, %2; }"
+                            : "+r"(a), "+r"(b), "+r"(c), "+r"(d), "+r"(e), "+r"(f), "+r"(g), "+r"(h));)
+BODY(k_i2f, { float fa, fb, fc, fd;
+  asm volatile("cvt.rn.f32.u32 %0, %4; cvt.rn.f32.u32 %1, %5; cvt.rn.f32.u32 %2, %6; cvt.rn.f32.u32 %3, %7;" : "=f"(fa), "=f"(fb), "=f"(fc), "=f"(fd) : "r"(a), "r"(b), "r"(c), "r"(d));
+  asm volatile("cvt.rzi.u32.f32 %0, %4; cvt.rzi.u32.f32 %1, %5; cvt.rzi.u32.f32 %2, %6; cvt.rzi.u32.f32 %3, %7;" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "f"(fa), "f"(fb), "f"(fc), "f"(fd)); })
+BODY(k_ffma_rm, { float fa = __uint_as_float(a), fb = __uint_as_float(b), fc = __uint_as_float(c), fd = __uint_as_float(d), fe = __uint_as_float(e), ff = __uint_as_float(f), fg = __uint_as_float(g), fh = __uint_as_float(h), fk = __uint_as_float(k);
+  asm volatile("fma.rm.f32 %0, %0, %8, %4; fma.rm.f32 %1, %1, %8, %5; fma.rm.f32 %2, %2, %8, %6; fma.rm.f32 %3, %3, %8, %7;"
+               "fma.rm.f32 %4, %4, %8, %0; fma.rm.f32 %5, %5, %8, %1; fma.rm.f32 %6, %6, %8, %2; fma.rm.f32 %7, %7, %8, %3;"
+               : "+f"(fa), "+f"(fb), "+f"(fc), "+f"(fd), "+f"(fe), "+f"(ff), "+f"(fg), "+f"(fh) : "f"(fk));
+  a = __float_as_uint(fa); b = __float_as_uint(fb); c = __float_as_uint(fc); d = __float_as_uint(fd); e = __float_as_uint(fe); f = __float_as_uint(ff); g = __float_as_uint(fg); h = __float_as_uint(fh); })
+BODY(k_dfma, { double da = (double)a, db = (double)b, dc = (double)c, dd = (double)d, dk = 1.0000001;
+  asm volatile("fma.rn.f64 %0, %0, %4, %1; fma.rn.f64 %1, %1, %4, %2; fma.rn.f64 %2, %2, %4, %3; fma.rn.f64 %3, %3, %4, %0;"
+               "fma.rn.f64 %0, %0, %4, %2; fma.rn.f64 %1, %1, %4, %3; fma.rn.f64 %2, %2, %4, %0; fma.rn.f64 %3, %3, %4, %1;"
+               : "+d"(da), "+d"(db), "+d"(dc), "+d"(dd) : "d"(dk));
+  a = (uint32_t)da; b = (uint32_t)db; c = (uint32_t)dc; d = (uint32_t)dd; })
+BODY(k_dfma_lop, { double da = (double)a, db = (double)b, dk = 1.0000001;
+  asm volatile("fma.rn.f64 %0, %0, %6, %1; lop3.b32 %2, %2, %3, %7, 0x96; lop3.b32 %3, %3, %4, %7, 0x96; lop3.b32 %4, %4, %5, %7, 0xe8;"
+               "fma.rn.f64 %1, %1, %6, %0; lop3.b32 %5, %5, %2, %7, 0x96; lop3.b32 %2, %2, %4, %7, 0x96; lop3.b32 %3, %3, %5, %7, 0xe8;"
+               : "+d"(da), "+d"(db), "+r"(c), "+r"(d), "+r"(e), "+r"(f) : "d"(dk), "r"(k));
+  a = (uint32_t)da; b = (uint32_t)db; })
+
 typedef void (*kern_t)(uint32_t *, uint32_t, unsigned long long *);
 
 int main()
@@ -115,6 +164,9 @@ int main()
     { "IMAD+LOP3 1:1", k_mix, 8 }, { "IMAD+LOP3 1:3", k_mix13, 8 },
     { "IMAD+IADD 1:1", k_imad_iadd, 8 }, { "IMAD+SHF 1:1", k_imad_shf, 8 }, { "LOP3+SHF 1:1", k_lop_shf, 8 }, { "FFMA", k_ffma, 8 },
     { "FFMA+LOP3 1:1", k_ffma_lop, 8 }, { "FFMA+IMAD 1:1", k_ffma_imad, 8 }, { "IMAD.HI+LOP3 1:3", k_hi_lop, 8 }, { "FLO+LOP3 1:7", k_flo_lop, 8 },
+    { "FSEL (selp.f32)", k_fsel, 8 }, { "SEL (selp.u32)", k_selp, 8 }, { "FADD/FMUL", k_fadd, 8 }, { "SHL 16 + ADD (LEA?)", k_lea, 8 }, { "PRMT", k_prmt, 8 },
+    { "predicated IADD", k_add_pred, 8 }, { "ISETP + @p IADD", k_setp, 8 }, { "IADD.CC + IADDC", k_iadd3x, 8 }, { "I2F + F2I", k_i2f, 8 },
+    { "FFMA.RM", k_ffma_rm, 8 }, { "DFMA", k_dfma, 8 }, { "DFMA+LOP3 1:3", k_dfma_lop, 8 },
   };
   for (auto &t : tests)
   {

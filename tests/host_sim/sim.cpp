@@ -68,15 +68,18 @@ uint64_t sim_check_div_table(uint32_t stride)
   for (uint32_t d = 3; d < (uint32_t)kDivTableEntries; d++)
   {
     for (uint64_t x = 0; x < (1ull << 30); x += stride)
-      bad += div_magic((uint32_t)x, t[d]) != (uint32_t)(x / d);
+      bad += div_magic((uint32_t)x, t[d], div_shift(d)) != (uint32_t)(x / d);
     const uint64_t edge[] = { (1ull << 30) - 1, (1ull << 29), (1ull << 29) - 1, 65536ull * 8192, 65535ull * 8191 };
     for (uint64_t x : edge)
-      bad += div_magic((uint32_t)x, t[d]) != (uint32_t)(x / d);
+      bad += div_magic((uint32_t)x, t[d], div_shift(d)) != (uint32_t)(x / d);
     for (uint64_t k = 1; k * d < (1ull << 30); k += 1 + stride / 64)   // multiples of d and their predecessors
     {
-      bad += div_magic((uint32_t)(k * d), t[d]) != (uint32_t)k;
-      bad += div_magic((uint32_t)(k * d - 1), t[d]) != (uint32_t)(k - 1);
+      bad += div_magic((uint32_t)(k * d), t[d], div_shift(d)) != (uint32_t)k;
+      bad += div_magic((uint32_t)(k * d - 1), t[d], div_shift(d)) != (uint32_t)(k - 1);
     }
+    bad += div_shift(d) != div_shift_host(d);
+    for (uint32_t x = 0; x <= 65536; x++)   // the shift-free form, every value the range can take (bac.c:109)
+      bad += div_small(x, t[d]) != x / d;
   }
   return bad;
 }
