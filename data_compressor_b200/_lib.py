@@ -33,7 +33,7 @@ ERROR_MESSAGES = {
 
 # enum dc_stage (include/dc_cuda.h)
 (STAGE_NORMALIZE, STAGE_DENORMALIZE, STAGE_DIFF_ENC, STAGE_DIFF_DEC, STAGE_SEG_ENC, STAGE_SEG_DEC,
- STAGE_BAC_ENC, STAGE_BAC_DEC, STAGE_LZMH_ENC, STAGE_LZMH_DEC, STAGE_DEGA_ENC, STAGE_DEGA_DEC) = range(12)
+ STAGE_BAC_ENC, STAGE_BAC_DEC, STAGE_LZMH_ENC, STAGE_LZMH_DEC, STAGE_DEGA_ENC, STAGE_DEGA_DEC, STAGE_COPY) = range(13)
 
 
 KERNEL_NAMES = ("front", "bac_encode", "scan", "gather", "bac_decode", "back", "lzmh_encode", "lzmh_decode")
@@ -42,7 +42,7 @@ KERNEL_NAMES = ("front", "bac_encode", "scan", "gather", "bac_decode", "back", "
 class Params(C.Structure):
     """dc_params: the subset of options_t (DCLib/inc/enc_dec.h:28-41) the hot path reads."""
     _fields_ = [("value_size_bits", C.c_uint32), ("normalization_factor", C.c_float),
-                ("adaptive", C.c_int32), ("reserved", C.c_uint32)]
+                ("adaptive", C.c_int32), ("block_size_bits", C.c_uint32)]
 
 
 class ContainerHeader(C.Structure):

@@ -117,8 +117,8 @@ class Context:
         self._check(self.lib.dc_synchronize(self.h), "dc_synchronize")
 
     @staticmethod
-    def _params(vs: int, nf: float, adaptive: bool) -> Params:
-        return Params(int(vs), float(nf), 1 if adaptive else 0, 0)
+    def _params(vs: int, nf: float, adaptive: bool, blocksize: int = 0) -> Params:
+        return Params(int(vs), float(nf), 1 if adaptive else 0, int(blocksize))
 
     @staticmethod
     def _layout(n_channels: int, channel_len: int, block_len: int) -> Layout:
@@ -340,14 +340,14 @@ class Context:
 
     # ---- plugin face: one stage, one stream, host bytes -------------------------------------------
     def stage_run(self, stage: int, data, nbits: int | None = None, vs: int = 32, nf: float = 100.0,
-                  adaptive: bool = False):
+                  adaptive: bool = False, blocksize: int = 0):
         """Runs ONE reference stage on the GPU (what an enc_dec_function_t body calls).  Returns
         (code, bytes, nbits): code is 0 or the negative err_codes.h value the reference stage returns."""
         src = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) \
             else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
         if nbits is None:
             nbits = src.size * 8
-        par = self._params(vs, nf, adaptive)
+        par = self._params(vs, nf, adaptive, blocksize)
         cap = int(self.lib.dc_stage_out_bound(stage, nbits, C.byref(par)))
         out_bits = C.c_uint64(0)
         for _ in range(3):
@@ -362,7 +362,7 @@ class Context:
         return rc, out[: (nb + 7) // 8].tobytes(), nb
 
     def chain_run(self, stages, data, nbits: int | None = None, vs: int = 32, nf: float = 100.0, adaptive: bool = False,
-                  out_cap: int | None = None):
+                  out_cap: int | None = None, blocksize: int = 0):
         """`encode X # encode Y # ...` over one stream with the intermediate results kept on the device
         (dc_chain_run_host).  `stages` is a list of stage numbers; the options apply to every stage, as when the
         command line repeats them.  Returns (code, bytes, nbits, failed_stage)."""
@@ -372,7 +372,7 @@ class Context:
             nbits = src.size * 8
         n = len(stages)
         st = (C.c_int * n)(*[int(x) for x in stages])
-        pars = (Params * n)(*[self._params(vs, nf, adaptive) for _ in range(n)])
+        pars = (Params * n)(*[self._params(vs, nf, adaptive, blocksize) for _ in range(n)])
         cap = out_cap or max(1 << 16, src.size * 40 + 4096)
         out_bits, failed = C.c_uint64(0), C.c_uint32(0)
         for _ in range(3):

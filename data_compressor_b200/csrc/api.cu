@@ -1960,6 +1960,7 @@ uint64_t dc_stage_out_bound(int stage, uint64_t in_bits, const dc_params *p)
     case DC_STAGE_LZMH_DEC: return in_bits / 10 * 274 / 2 + 4096;
     case DC_STAGE_DEGA_ENC: return (in_bits / 32 * (2 * vs + 1) * 13 / 8 + 7) / 8 + 64;
     case DC_STAGE_DEGA_DEC: return in_bits * 16 + 4096;
+    case DC_STAGE_COPY: return (in_bits + 7) / 8 + 8;
     default: return 0;
   }
 }
@@ -1975,6 +1976,28 @@ static int stage_run(dc_ctx *c, int stage, const uint8_t *in, cudaMemcpyKind in_
   CU_TRY(c, cudaSetDevice(c->device), DC_ERR_LIBRARY_INIT);
   if (stage == DC_STAGE_LZMH_ENC || stage == DC_STAGE_LZMH_DEC)
     return lzmh_stage_host(c, stage == DC_STAGE_LZMH_ENC, in, in_kind, in_bits, out, out_kind, out_cap, out_bits);
+  if (stage == DC_STAGE_COPY)
+  {
+    // Copy (copy.c:11-29) moves block_size_bits at a time and fails with ERROR_LIBRARY_CALL on a short last block
+    // (READ_BITS_CHECKED, io_macros.h:13-27); a stream of whole blocks comes out unchanged.  Inside a chain that is one
+    // device-to-device copy: the stage exists so that a command line that names it stays on the device.
+    const uint64_t block = params->block_size_bits ? params->block_size_bits : 8;
+    if (in_bits % block != 0)
+      return DC_ERR_LIBRARY_CALL;
+    const uint64_t nbytes = (in_bits + 7) / 8;
+    *out_bits = in_bits;
+    if (nbytes > out_cap)
+    {
+      set_err(c, "stage output needs %llu bytes, capacity is %llu", (unsigned long long)nbytes, (unsigned long long)out_cap);
+      return DC_ERR_MEMORY;
+    }
+    if (nbytes)
+    {
+      CU_TRY(c, cudaMemcpyAsync(out, in, nbytes, cudaMemcpyDefault, c->stream), DC_ERR_LIBRARY_CALL);
+      CU_TRY(c, cudaStreamSynchronize(c->stream), DC_ERR_LIBRARY_CALL);
+    }
+    return DC_OK;
+  }
 
   const uint32_t vs = params->value_size_bits;
   const uint64_t in_bytes = (in_bits + 7) / 8;

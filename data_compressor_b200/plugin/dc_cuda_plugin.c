@@ -100,7 +100,7 @@ static io_int_t RunStage(const int stage, bit_file_buffer_t * const in_bit_buf, 
   params.value_size_bits = (uint32_t)options->value_size_bits;
   params.normalization_factor = options->normalization_factor;
   params.adaptive = options->adaptive;
-  params.reserved = 0;
+  params.block_size_bits = (uint32_t)options->block_size_bits;
   out_capacity = dc_stage_out_bound(stage, in_bits, &params);
   out_data = NULL;
   for (attempt = 0; attempt < 2; attempt++)
@@ -170,6 +170,100 @@ DEFINE_STAGE_PLUGIN(EncodeBAC, EncodeBAC_CUDA, DC_STAGE_BAC_ENC)                
 DEFINE_STAGE_PLUGIN(DecodeBAC, DecodeBAC_CUDA, DC_STAGE_BAC_DEC)                               /* bac.c:244      */
 DEFINE_STAGE_PLUGIN(EncodeLZMH, EncodeLZMH_CUDA, DC_STAGE_LZMH_ENC)                            /* lzmh.c:130     */
 DEFINE_STAGE_PLUGIN(DecodeLZMH, DecodeLZMH_CUDA, DC_STAGE_LZMH_DEC)                            /* lzmh.c:383     */
+DEFINE_STAGE_PLUGIN(Copy, Copy_CUDA, DC_STAGE_COPY)                                            /* copy.c:11      */
+
+/* ---- chains: several stages of one command line as ONE device-resident chain (dc_chain_run_host) ----------------- */
+/* Which DC_STAGE_* value a registry function of this file runs; -1 for any other function (the csv plugins below, the
+   reference's own codecs): those are stages a chain fuser leaves alone. */
+int DcCudaStageOf(enc_dec_function_t * const function, const int encode)
+{
+  static const struct { enc_dec_function_t *function; int stage; } stages[] =
+  {
+    { PLUGIN_NAME(Normalize, Normalize_CUDA), DC_STAGE_NORMALIZE }, { PLUGIN_NAME(Denormalize, Denormalize_CUDA), DC_STAGE_DENORMALIZE },
+    { PLUGIN_NAME(EncodeDifferential, EncodeDifferential_CUDA), DC_STAGE_DIFF_ENC }, { PLUGIN_NAME(DecodeDifferential, DecodeDifferential_CUDA), DC_STAGE_DIFF_DEC },
+    { PLUGIN_NAME(EncodeSEG, EncodeSEG_CUDA), DC_STAGE_SEG_ENC }, { PLUGIN_NAME(DecodeSEG, DecodeSEG_CUDA), DC_STAGE_SEG_DEC },
+    { PLUGIN_NAME(EncodeBAC, EncodeBAC_CUDA), DC_STAGE_BAC_ENC }, { PLUGIN_NAME(DecodeBAC, DecodeBAC_CUDA), DC_STAGE_BAC_DEC },
+    { PLUGIN_NAME(EncodeLZMH, EncodeLZMH_CUDA), DC_STAGE_LZMH_ENC }, { PLUGIN_NAME(DecodeLZMH, DecodeLZMH_CUDA), DC_STAGE_LZMH_DEC },
+    { PLUGIN_NAME(Copy, Copy_CUDA), DC_STAGE_COPY }, { EncodeDEGA_CUDA, DC_STAGE_DEGA_ENC }, { DecodeDEGA_CUDA, DC_STAGE_DEGA_DEC }
+  };
+  size_t i;
+  (void)encode;
+  for (i = 0; i < sizeof(stages) / sizeof(stages[0]); i++)
+    if (stages[i].function == function)
+      return stages[i].stage;
+  return -1;
+}
+
+/* Runs `count` consecutive stages of a parsed command line (their options_t in order, DCCLI/inc/params.h:12-17) with one
+   copy to the device and one copy back: drains `in_bit_buf`, writes the exact result bits to `out_bit_buf`.  Every stage
+   must be one DcCudaStageOf() knows.  On failure *failed_stage is the index of the stage that failed, with the code the
+   reference's stage would have returned. */
+io_int_t DcCudaRunChain(options_t * const * const options, const size_t count, bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf,
+                        size_t * const failed_stage)
+{
+  dc_ctx *ctx;
+  dc_params params[16]; /* MAX_OPTIONS, DCCLI/inc/params.h:10 */
+  int stages[16];
+  uint8_t *in_data, *out_data = NULL;
+  io_uint_t in_bits;
+  uint64_t out_bits = 0, out_capacity;
+  uint32_t failed = 0;
+  io_int_t ret;
+  size_t i;
+  int attempt;
+  FILE * const error_log_file = options[0]->error_log_file;
+  *failed_stage = 0;
+  if (count == 0 || count > 16)
+    return ERROR_INVALID_VALUE;
+  for (i = 0; i < count; i++)
+  {
+    enc_dec_function_t * const function = options[i]->encode ? options[i]->encoder_decoder->encoder : options[i]->encoder_decoder->decoder;
+    if ((stages[i] = DcCudaStageOf(function, options[i]->encode)) < 0)
+    {
+      *failed_stage = i;
+      return ERROR_INVALID_MODE;
+    }
+    params[i].value_size_bits = (uint32_t)options[i]->value_size_bits;
+    params[i].normalization_factor = options[i]->normalization_factor;
+    params[i].adaptive = options[i]->adaptive;
+    params[i].block_size_bits = (uint32_t)options[i]->block_size_bits;
+  }
+  if ((ret = GetContext(&ctx, error_log_file)) != NO_ERROR)
+    return ret;
+  if ((ret = DrainInput(in_bit_buf, &in_data, &in_bits)) != NO_ERROR)
+    return ret;
+  out_capacity = (in_bits + 7) / 8 * 8 + (1 << 16);
+  for (attempt = 0; attempt < 2; attempt++)
+  {
+    if ((out_data = (uint8_t*)malloc((size_t)out_capacity + 16)) == NULL)
+    {
+      free(in_data);
+      return ERROR_MEMORY;
+    }
+    ret = dc_chain_run_host(ctx, (uint32_t)count, stages, params, in_data, in_bits, out_data, out_capacity, &out_bits, &failed);
+    if (ret != DC_ERR_MEMORY || failed + 1 != count || out_bits == 0)
+      break;
+    free(out_data); /* The last stage reported the exact size it needs: once more with that */
+    out_data = NULL;
+    out_capacity = (out_bits + 7) / 8 + 16;
+  }
+  free(in_data);
+  if (ret != NO_ERROR)
+  {
+    if (out_data != NULL)
+      free(out_data);
+    *failed_stage = failed;
+    if (ret == ERROR_LIBRARY_CALL || ret == ERROR_LIBRARY_INIT)
+      LOG_ERROR(error_log_file, "CUDA chain failed at its stage %lu: %s\n", (unsigned long)(failed + 1), dc_last_error(ctx));
+    return ret;
+  }
+  if (out_bits > 0)
+  {
+    WRITE_BITS_CHECKED_WITH_ACTION_ON_ERROR(out_data, (size_t)out_bits, out_bit_buf, error_log_file, free(out_data));
+  }
+  free(out_data);
+  return NO_ERROR;
+}
 
 /* ---- text input ------------------------------------------------------------------------------------------------ */
 /* `decode csv [column=..] [separator_char=..]` (csv.c:13).  csv.c defines ReadCSV and WriteCSV in one file, so this one

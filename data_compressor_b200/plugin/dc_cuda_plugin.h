@@ -18,6 +18,12 @@ io_int_t EncodeBAC_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t 
 io_int_t DecodeBAC_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options);
 io_int_t EncodeLZMH_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options);
 io_int_t DecodeLZMH_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options);
+io_int_t Copy_CUDA(bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf, const options_t * const options);
 #endif
+
+/* For a chain fuser on the CLI side (dc_fused_main.c) */
+int DcCudaStageOf(enc_dec_function_t * const function, const int encode);
+io_int_t DcCudaRunChain(options_t * const * const options, const size_t count, bit_file_buffer_t * const in_bit_buf, bit_file_buffer_t * const out_bit_buf,
+                        size_t * const failed_stage);
 
 #endif

@@ -45,7 +45,7 @@ typedef struct dc_params
   uint32_t value_size_bits;       /* options_t.value_size_bits, 1..64, default 32 (enc_dec.c:187-197) */
   float    normalization_factor;  /* options_t.normalization_factor, default 100 */
   int32_t  adaptive;              /* options_t.adaptive (bac only), default 0 */
-  uint32_t reserved;
+  uint32_t block_size_bits;       /* options_t.block_size_bits (copy only), default 8 (enc_dec.c:187-197); 0 = that default */
 } dc_params;
 
 /* Where the streams live inside one flat sample array (channel-major, one channel after another,
@@ -277,6 +277,7 @@ enum dc_stage
   DC_STAGE_LZMH_DEC,        /* decode lzmh       : DecodeLZMH           lzmh.c:383-574    */
   DC_STAGE_DEGA_ENC,        /* fused normalize # diff # seg # bac                           */
   DC_STAGE_DEGA_DEC,        /* fused bac # seg # diff # normalize (decode)                  */
+  DC_STAGE_COPY,            /* encode / decode copy [blocksize=..] : Copy    copy.c:11-29   */
   DC_STAGE_COUNT
 };
 

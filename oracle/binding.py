@@ -22,6 +22,7 @@ REF_CLI = os.path.join(HERE, "_ref", "DCCLI")
 
 # enum dco_stage_id (oracle/dc_oracle.h)
 NORMALIZE, DENORMALIZE, DIFF_ENC, DIFF_DEC, SEG_ENC, SEG_DEC, BAC_ENC, BAC_DEC, LZMH_ENC, LZMH_DEC = range(10)
+COPY = 12   # DCO_COPY == DC_STAGE_COPY
 
 #: oracle stage id -> (DCCLI encoder name, encode flag)   (DCLib/src/enc_dec.c:51-60)
 STAGE_TO_CLI = {
@@ -30,6 +31,7 @@ STAGE_TO_CLI = {
     SEG_ENC: ("seg", 1), SEG_DEC: ("seg", 0),
     BAC_ENC: ("bac", 1), BAC_DEC: ("bac", 0),
     LZMH_ENC: ("lzmh", 1), LZMH_DEC: ("lzmh", 0),
+    COPY: ("copy", 1),
 }
 
 DEGA_ENC = [NORMALIZE, DIFF_ENC, SEG_ENC, BAC_ENC]
@@ -64,6 +66,10 @@ class Oracle:
         L.dco_aggregate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p]
         L.dco_dega_encode_batch.restype = C.c_int64
         L.dco_dega_encode_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_float, C.c_int]
+
+    def set_block_size(self, bits: int) -> None:
+        """`blocksize` of the copy stages in the chains run from now on (default 8)."""
+        self.lib.dco_set_block_size(C.c_uint(int(bits)))
 
     def run_chain(self, stages, data, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
         src = _as_u8(data)
@@ -177,6 +183,11 @@ class Ref:
         if n < 0:
             raise RuntimeError(f"reference aggregate failed: {n}")
         return out[:n].copy()
+
+    def set_block_size(self, bits: int) -> None:
+        if not hasattr(self.lib, "ref_set_block_size"):
+            raise RuntimeError("oracle/_ref/libdcref.so predates ref_set_block_size: rebuild it where /root/reference exists")
+        self.lib.ref_set_block_size(C.c_uint(int(bits)))
 
     def run_chain(self, stages, data, nbits=None, vs=32, nf=100.0, adaptive=1, out_cap=None):
         src = _as_u8(data)

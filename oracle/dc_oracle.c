@@ -868,6 +868,36 @@ int dco_lzmh_decode(const dco_bits *in, dco_bits *out)
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Copy, DCLib/src/copy.c:11-29: blocks of block_bits bits are read and written unchanged until the input ends
+   (copy.c:22-26); a short last block is a failed read (READ_BITS_CHECKED, io_macros.h:13-27), after the whole blocks
+   before it have been written.  Blocks may be any size: they are moved 64 bits at a time here. */
+int dco_copy(const dco_bits *in, dco_bits *out, unsigned block_bits)
+{
+  bit_reader r;
+  if (block_bits == 0)
+    return DCO_ERR_INVALID_VALUE;
+  rd_init(&r, in);
+  while (!rd_eof(&r))
+  {
+    uint64_t left = block_bits;
+    if (r.nbits - r.pos < left)                                     /* copy.c:24 */
+      return DCO_ERR_LIBRARY_CALL;
+    while (left > 0)
+    {
+      const unsigned n = left > 64 ? 64u : (unsigned)left;
+      uint64_t v;
+      int ret;
+      if ((ret = get_bits(&r, n, &v)) != DCO_OK || (ret = put_bits(out, v, n)) != DCO_OK)   /* copy.c:24-25 */
+        return ret;
+      left -= n;
+    }
+  }
+  return DCO_OK;
+}
+
+static unsigned g_block_bits = 8;                                   /* enc_dec.c:187-197: blocksize defaults to 8 */
+void dco_set_block_size(unsigned bits) { g_block_bits = bits ? bits : 8; }
+
 /* Chains (DCCLI/src/cli.c:430-466: every stage runs to completion, exact-bit hand-off) */
 
 static int run_stage(int id, const dco_bits *in, dco_bits *out, unsigned vs, float nf, int adaptive)
@@ -884,6 +914,7 @@ static int run_stage(int id, const dco_bits *in, dco_bits *out, unsigned vs, flo
     case DCO_BAC_DEC:     return dco_bac_decode(in, out, adaptive);
     case DCO_LZMH_ENC:    return dco_lzmh_encode(in, out);
     case DCO_LZMH_DEC:    return dco_lzmh_decode(in, out);
+    case DCO_COPY:        return dco_copy(in, out, g_block_bits);
     default:              return DCO_ERR_INVALID_VALUE;
   }
 }

@@ -55,6 +55,7 @@ int dco_bac_encode(const dco_bits *in, dco_bits *out, int adaptive);            
 int dco_bac_decode(const dco_bits *in, dco_bits *out, int adaptive);                   /* bac.c:171-264     */
 int dco_lzmh_encode(const dco_bits *in, dco_bits *out);                                /* lzmh.c:130-370    */
 int dco_lzmh_decode(const dco_bits *in, dco_bits *out);                                /* lzmh.c:383-574    */
+int dco_copy(const dco_bits *in, dco_bits *out, unsigned block_bits);                  /* copy.c:11-29      */
 
 /* Flat-buffer conveniences for ctypes.  `out` must hold out_cap bytes; *out_bits receives the exact
    bit count (bytes = ceil(bits/8), zero padded).  Return code as above; DCO_ERR_MEMORY if out_cap is
@@ -62,8 +63,12 @@ int dco_lzmh_decode(const dco_bits *in, dco_bits *out);                         
 enum dco_stage_id
 {
   DCO_NORMALIZE = 0, DCO_DENORMALIZE, DCO_DIFF_ENC, DCO_DIFF_DEC, DCO_SEG_ENC, DCO_SEG_DEC,
-  DCO_BAC_ENC, DCO_BAC_DEC, DCO_LZMH_ENC, DCO_LZMH_DEC
+  DCO_BAC_ENC, DCO_BAC_DEC, DCO_LZMH_ENC, DCO_LZMH_DEC,
+  DCO_COPY = 12   /* same number as DC_STAGE_COPY of include/dc_cuda.h (10 and 11 are that header's fused chains) */
 };
+
+/* `blocksize` of the copy stages of the chains run from now on (options_t.block_size_bits, default 8: enc_dec.c:187-197) */
+void dco_set_block_size(unsigned bits);
 
 /* Runs `nstages` stages back to back with exact-bit hand-off (what DCCLI's stage loop does,
    DCCLI/src/cli.c:430-466).  adaptive applies to the bac stages, vs/nf to the others. */

@@ -50,6 +50,9 @@ static void mem_bits_close(mem_bits *m)
   m->bb = NULL;
 }
 
+static size_t g_block_size_bits = 8;   /* `blocksize` of the copy stages (options_t.block_size_bits), default as enc_dec.c:187-197 */
+void ref_set_block_size(unsigned bits) { g_block_size_bits = bits ? bits : 8; }
+
 /* Runs `nstages` reference stages back to back.
    names[i]   : encoder name as given on the DCCLI command line ("normalize", "diff", "seg", "bac", "lzmh", ...)
    encode[i]  : 1 = "encode <name>", 0 = "decode <name>"
@@ -106,6 +109,7 @@ long long ref_run_chain(const char *const *names, const int *encode, int nstages
     opt.value_size_bits = vs;
     opt.normalization_factor = nf;
     opt.adaptive = adaptive;
+    opt.block_size_bits = g_block_size_bits;
     fn = encode[i] ? ed->encoder : ed->decoder;
     if (fn == NULL)
     {

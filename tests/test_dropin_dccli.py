@@ -79,3 +79,49 @@ def test_csv_reader_behind_the_unchanged_registry_row(testfile, options):
     assert run(CPU, src, a, chain) == 0
     assert run(GPU, src, b, chain) == 0
     assert open(a, "rb").read() == open(b, "rb").read() and os.path.getsize(a) > 0
+
+
+def run_env(binary, src, dst, chain, **env):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([binary, src, dst] + chain.split(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=e)
+    return r.returncode, r.stderr.decode(errors="replace")
+
+
+@pytest.mark.parametrize("chain,pieces", [
+    (DEGA + " # " + UNDEGA, 3),                                   # csv | eight GPU stages as one chain | csv
+    (DEGA, 2),
+    ("encode normalize # encode copy # encode diff # encode copy blocksize=32 # encode seg # encode bac adaptive", 1),
+    ("encode lzmh # decode lzmh # encode copy blocksize=16", 1),
+    ("encode copy blocksize=24", None),                           # a single stage: nothing to fuse, the reference's own main runs it
+])
+def test_chain_fuser_in_front_of_the_stage_loop(testfile, golden, chain, pieces):
+    """dc_fused_main.c (linked in front of the unmodified cli.c) runs every run of consecutive GPU stages of a command
+    line as ONE device-resident chain; the result is the file the stage-by-stage path (DC_CUDA_NO_FUSE) and the CPU
+    DCCLI write, and the report says how many pieces the command line was cut into."""
+    d, src = testfile
+    if not chain.startswith("decode csv"):
+        src = str(d / "input.f32")
+        golden.testfile[:6000].tofile(src)      # raw float32 in (24 000 bytes: whole 16-, 24- and 32-bit blocks)
+    a, b, c = str(d / "f_cpu.bin"), str(d / "f_fused.bin"), str(d / "f_staged.bin")
+    assert run(CPU, src, a, chain) == 0
+    rc, err = run_env(GPU, src, b, chain, DC_CUDA_FUSE_REPORT="1")
+    assert rc == 0, err
+    if pieces is not None:
+        assert f"{len(chain.split('#'))} stages in {pieces} pieces" in err
+    else:
+        assert "dc_fused_main" not in err
+    rc, err = run_env(GPU, src, c, chain, DC_CUDA_NO_FUSE="1")
+    assert rc == 0, err
+    assert open(a, "rb").read() == open(b, "rb").read() == open(c, "rb").read()
+
+
+def test_chain_fuser_reports_the_failing_stage_like_the_reference(testfile):
+    d, _ = testfile
+    src = str(d / "odd.bin")
+    open(src, "wb").write(bytes(range(7)))       # 56 bits: not a whole number of 32-bit blocks
+    chain = "encode copy # encode copy blocksize=32 # encode copy"
+    rc_cpu = run(CPU, src, str(d / "o_cpu.bin"), chain)
+    rc_gpu, err = run_env(GPU, src, str(d / "o_gpu.bin"), chain)
+    assert rc_cpu == rc_gpu != 0
+    assert "encoder/decoder 2 of 3" in err

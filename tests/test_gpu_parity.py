@@ -730,6 +730,36 @@ def test_chain_run_matches_oracle_chain(ctx, oracle, golden, vs, adaptive):
             oracle.run_chain(mixed + [ob.LZMH_DEC, ob.DIFF_DEC], x, x.size * 32, out_cap=1 << 22)
 
 
+def test_copy_stage_and_chains_that_contain_it(ctx, oracle):
+    """`copy` (DCLib/src/copy.c:11-29) as a device stage: whole blocks pass unchanged, a short last block fails like the
+    reference's checked read, and a chain that names it keeps its intermediate results on the device."""
+    rng = np.random.default_rng(33)
+    for bs, nbits in [(8, 800), (8, 803), (13, 13 * 50), (13, 700), (64, 6400), (1, 777), (24, 0), (0, 64)]:
+        data = rng.integers(0, 256, (nbits + 7) // 8, dtype=np.uint8)
+        if nbits % 8:
+            data[-1] &= (0xFF00 >> (nbits % 8)) & 0xFF
+        oracle.set_block_size(bs)
+        want = oracle.run_chain([ob.COPY], data, nbits)
+        got = ctx.stage_run(ob.COPY, data, nbits, blocksize=bs)
+        assert got[0] == want[0], (bs, nbits)
+        if want[0] == 0:
+            assert got == want, (bs, nbits)
+    x = profile(rng, 3000)
+    oracle.set_block_size(32)
+    chain = [ob.NORMALIZE, ob.COPY, ob.DIFF_ENC, ob.SEG_ENC, ob.COPY, ob.BAC_ENC]
+    want = oracle.run_chain(chain, x, 3000 * 32, 32, 100.0, 1)
+    oracle.set_block_size(8)
+    # the SEG stream is not a whole number of 32-bit blocks in general: the second copy decides the outcome
+    got = ctx.chain_run(chain, x, None, 32, 100.0, True, blocksize=32)
+    assert got[0] == want[0] and (want[0] != 0 or got[:3] == want)
+    want8 = oracle.run_chain(chain, x, 3000 * 32, 32, 100.0, 1)
+    got8 = ctx.chain_run(chain, x, None, 32, 100.0, True, blocksize=1)
+    oracle.set_block_size(1)
+    want1 = oracle.run_chain(chain, x, 3000 * 32, 32, 100.0, 1)
+    oracle.set_block_size(8)
+    assert want1[0] == 0 and got8[:3] == want1 and (want8[0] != 0 or want8 == want1)
+
+
 def test_chain_run_errors_and_edges(ctx, oracle):
     """The chain stops at the stage the reference would stop at, with its code; empty input; one stage; too many stages."""
     x = np.array([1.0, -2.5, 3.0], dtype=np.float32)            # a negative sample: diff refuses it (diff.c:17-18)

@@ -153,3 +153,21 @@ def test_csv_round_trip_of_the_test_file(oracle, ref, golden):
     """decode csv # encode csv gives the test file's text back (what `make test` diffs at the end)."""
     text = "".join(f"{v:.2f}\n" for v in golden.testfile)
     assert ref.csv_encode(ref.csv_decode(text)) == text.encode() == oracle.csv_encode(oracle.csv_decode(text))
+
+
+def test_copy_stage_matches_the_reference(oracle, ref):
+    """`encode copy blocksize=..` (DCLib/src/copy.c:11-29): whole blocks pass, a short last block is a failed read after
+    the whole blocks before it were written."""
+    rng = np.random.default_rng(77)
+    try:
+        for bs in (1, 5, 8, 13, 32, 64, 100, 1000):
+            for nbits in (0, bs, 3 * bs, 3 * bs + 1, 10 * bs - 1, 997):
+                data = rng.integers(0, 256, (nbits + 7) // 8, dtype=np.uint8)
+                if nbits % 8:
+                    data[-1] &= (0xFF00 >> (nbits % 8)) & 0xFF
+                oracle.set_block_size(bs)
+                ref.set_block_size(bs)
+                assert oracle.run_chain([ob.COPY], data, nbits) == ref.run_chain([ob.COPY], data, nbits), (bs, nbits)
+    finally:
+        oracle.set_block_size(8)
+        ref.set_block_size(8)
