@@ -696,24 +696,50 @@ def run_secondary(args):
 # two decimals so that the reference round trip stays bit-exact: sums themselves leave float32's exact range).
 def run_sweep(args):
     import torch
+    import torch.distributed as dist
     from data_compressor_b200 import Context, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: data_compressor_b200 has no CPU fallback")
-    dev = torch.device("cuda", 0)
-    ctx = Context(0)
+    # weak scaling like the headline workload: every rank sweeps its own 4096 channels (own seed) on its own GPU, a
+    # point's time is the slowest rank's; rank 0 prints, and times the reference on the host cores once per granularity
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local)
     ctx.set_profiling(True)
     steps, warm = max(1, min(args.steps, 5)), 2
-    x1 = synth.redd_like(args.channels, SAMPLES, device=dev)
+    x1 = synth.redd_like(args.channels, SAMPLES, device=dev, seed=0xDC0000 + rank * args.channels)
     hundred = torch.tensor(100.0, dtype=torch.float32, device=dev)
     series = {"1s": x1}
     for name, k in (("1min", 60), ("15min", 900)):
         a = ctx.aggregate(x1, k) / float(k)                                   # mean power of the interval
         series[name] = (torch.round(a * hundred) / hundred).contiguous()     # two decimals again: exact reference round trip
+    kind, cores = None, os.cpu_count() or 1
+    if rank == 0 and not args.no_cpu:
+        from oracle import binding as ob
+        ob.build(ref=os.path.isdir("/root/reference/DataCompressor"))
+        kind = cpu_kind()
     for gran, x in series.items():
         n = x.shape[1]
+        cpu = None
+        if kind is not None:
+            # the reference on whole series of this granularity (one plain DCCLI-style run per channel), a bounded sample
+            per_core = max(1, int(args.cpu_seconds * 0.9e6 / (n * 4)))
+            rows = x[: min(x.shape[0], per_core * cores)].cpu().numpy()
+            g, busy, wall = cpu_baseline_run([r.copy() for r in rows], cores, kind)
+            cpu = {"value": g, "unit": "GB/s", "cores": cores, "kind": kind, "seconds": busy,
+                   "sample": f"{rows.shape[0]} whole channels of {n} samples ({rows.nbytes / 1e6:.1f} MB raw), valuesize 32, encode+decode, one worker process per core"}
         for vs in (17, 24, 32, 64):
-            if float(x.max().item()) * 100.0 + 0.5 > float(2 ** (vs - 1) - 1):
-                continue      # normalize.c:21-22 would reject the series at this value size
+            ok_vs = torch.tensor([float(x.max().item()) * 100.0 + 0.5 <= float(2 ** (vs - 1) - 1)], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(ok_vs, op=dist.ReduceOp.MIN)
+            if not bool(ok_vs.item()):
+                continue      # normalize.c:21-22 would reject the series at this value size (on some rank)
             for bl in (0, 16384, 4096, 1024):
                 if bl >= n and bl != 0:
                     continue
@@ -729,13 +755,26 @@ def run_sweep(args):
                         t_dec += sum(k2[k] for k in ("bac_decode", "back"))
                 ok = bool(torch.equal(y.view(torch.int32), x.view(torch.int32))) and not bool(enc.status.any().item())
                 raw = x.numel() * 4
-                enc_ms, dec_ms = t_enc / steps, t_dec / steps
-                print(json.dumps({
-                    "metric": "DEGA encode / decode GB/s of raw samples (configs[4] sweep)", "granularity": gran, "samples_per_channel": n,
-                    "channels": args.channels, "valuesize": vs, "block_len": bl, "streams": enc.n_streams, "encode_ms": enc_ms,
-                    "decode_ms": dec_ms, "encode_gbs": raw / (enc_ms * 1e-3) / 1e9, "decode_gbs": raw / (dec_ms * 1e-3) / 1e9,
-                    "compression_ratio": raw / enc.total_bytes, "round_trip_ok": ok, "n_gpus": 1, "steps": steps, "data": "synthetic"}), flush=True)
+                t = torch.tensor([t_enc / steps, t_dec / steps, -float(ok)], dtype=torch.float64, device=dev)
+                tot = torch.tensor([float(enc.total_bytes)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                enc_ms, dec_ms, ok = float(t[0].item()), float(t[1].item()), float(t[2].item()) == -1.0
+                if rank == 0:
+                    line = {
+                        "metric": "DEGA encode / decode GB/s of raw samples (configs[4] sweep)", "granularity": gran, "samples_per_channel": n,
+                        "channels_per_gpu": args.channels, "valuesize": vs, "block_len": bl, "streams_per_gpu": enc.n_streams, "encode_ms": enc_ms,
+                        "decode_ms": dec_ms, "encode_gbs": world * raw / (enc_ms * 1e-3) / 1e9, "decode_gbs": world * raw / (dec_ms * 1e-3) / 1e9,
+                        "value": world * raw / ((enc_ms + dec_ms) * 1e-3) / 1e9, "unit": "GB/s",
+                        "compression_ratio": world * raw / float(tot.item()), "round_trip_ok": ok, "n_gpus": world, "steps": steps, "scaling": "weak",
+                        "data": "synthetic"}
+                    if vs == 32 and bl == 0:
+                        line["cpu_baseline"] = cpu
+                    print(json.dumps(line), flush=True)
                 del y
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -418,6 +418,202 @@ __global__ void __launch_bounds__(256) axdr_decode32_kernel(const AxdrArgs a, co
   }
 }
 
+// ---- A-XDR, value sizes below 32: the records of equal-length streams are whole words, so the payload is one flat
+// string of vs-bit fields and a tile of 1024 samples is exactly 32 * vs words whatever the stream length.  A CTA loads a
+// tile with 128-bit loads, normalises every sample once into shared memory, then every thread assembles whole output
+// words from it: all global traffic is coalesced and each sample is read once (the general kernel above loads a sample
+// once per word it touches, scalar).  Memory bound: 4 B in + vs / 8 B out per sample.
+static const int kAxdrTile = 1024;
+
+// normalize.c:16-23 for a value size below 32; n = the low 32 bits of the truncated value
+__device__ __forceinline__ bool normalize_small(float v, float nf, float lo_bound, float hi_bound, uint32_t &n)
+{
+  if (v > 0.0f)
+    v = __fadd_rn(__fmul_rn(v, nf), 0.5f);
+  else if (v < 0.0f)
+    v = __fsub_rn(__fmul_rn(v, nf), 0.5f);
+  const bool ok = v >= lo_bound && v <= hi_bound;   // |v| <= 2^30 when it holds (NaN fails)
+  n = ok ? (uint32_t)__float2int_rz(v) : 0u;
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) axdr_encode_tiled_kernel(const AxdrArgs a, const uint64_t total_samples)
+{
+  __shared__ uint32_t vals[kAxdrTile];
+  const uint32_t vs = a.vs, mask = (1u << vs) - 1u;
+  const float lo_bound = -(float)(1u << (vs - 1));
+  const float hi_bound = (float)((1u << (vs - 1)) - 1);
+  const uint32_t tid = threadIdx.x;
+  const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + tid; s < a.n_streams; s += gsize)   // the index: equal records
+  {
+    a.bit_len[s] = a.len * vs;
+    a.byte_off[s] = s * a.words_per_stream * 4ull;
+  }
+  if (blockIdx.x == 0 && tid == 0)
+    a.byte_off[a.n_streams] = a.n_streams * a.words_per_stream * 4ull;
+  const uint64_t n_tiles = (total_samples + kAxdrTile - 1) / kAxdrTile;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const uint64_t base = tile * kAxdrTile;
+    const uint32_t here = (uint32_t)min((uint64_t)kAxdrTile, total_samples - base);
+    float f[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    const uint32_t i = 4 * tid;
+    if (i + 4 <= here)
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(a.samples_in + base) + tid);
+      f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    else
+      for (uint32_t j = 0; j < 4; j++)
+        if (i + j < here)
+          f[j] = __ldg(a.samples_in + base + i + j);
+    bool ok = true;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++)
+    {
+      uint32_t n;
+      const bool okj = normalize_small(f[j], a.nf, lo_bound, hi_bound, n);
+      vals[i + j] = n & mask;
+      if (!okj && i + j < here)
+      {
+        a.status[(base + i + j) / a.len] = DC_ERR_INVALID_VALUE_D;
+        ok = false;
+      }
+    }
+    if (!ok)
+      atomicExch(a.err_flag, 1ull);   // the caller redoes the batch on the general path (a failed stream changes the layout)
+    __syncthreads();
+    const uint32_t n_words = here * vs / 32;   // exact: tiles and the whole batch are whole words
+    uint32_t *out = a.payload_words + base / 32 * vs;
+    for (uint32_t w = tid; w < n_words; w += 256)
+    {
+      const uint32_t bit0 = w * 32;
+      uint32_t k = bit0 / vs;
+      uint32_t nb = vs - (bit0 - k * vs);            // bits of field k that belong to this word (and the ones after it)
+      uint64_t acc = vals[k++] & ((1u << nb) - 1u);
+      while (nb < 32)
+      {
+        acc = (acc << vs) | vals[k++];
+        nb += vs;
+      }
+      out[w] = bswap32((uint32_t)(acc >> (nb - 32)));
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) axdr_decode_tiled_kernel(const AxdrArgs a, const uint64_t total_samples)
+{
+  __shared__ uint32_t words[kAxdrTile + 1];   // a tile of 1024 samples is 32 * vs <= 992 words; one more for the last field's window
+  const uint32_t vs = a.vs;
+  const uint32_t tid = threadIdx.x;
+  const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + tid; s < a.n_streams; s += gsize)
+  {
+    a.n_out[s] = a.len;
+    a.status[s] = 0;
+  }
+  const uint32_t *in = reinterpret_cast<const uint32_t *>(a.payload);
+  const uint64_t n_tiles = (total_samples + kAxdrTile - 1) / kAxdrTile;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const uint64_t base = tile * kAxdrTile;
+    const uint32_t here = (uint32_t)min((uint64_t)kAxdrTile, total_samples - base);
+    const uint32_t n_words = here * vs / 32;
+    const uint32_t *src = in + base / 32 * vs;
+    for (uint32_t w = tid; w < n_words; w += 256)
+      words[w] = bswap32(__ldg(src + w));
+    if (tid == 0)
+      words[n_words] = 0;
+    __syncthreads();
+    const uint32_t i = 4 * tid;
+    float f[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++)
+    {
+      const uint32_t bit = (i + j) * vs, w = min(bit >> 5, n_words - (n_words ? 1u : 0u)), sh = bit & 31;
+      const uint64_t win = ((uint64_t)words[w] << 32) | words[w + 1];
+      const uint32_t u = (uint32_t)((win << sh) >> (64 - vs));
+      const int32_t v = (int32_t)(u << (32 - vs)) >> (32 - vs);   // EXTEND_IO_INT_SIGN, io_macros.h:89-90
+      f[j] = __fdiv_rn(__int2float_rn(v), a.nf);                  // normalize.c:36-39
+    }
+    if (i + 4 <= here)
+      reinterpret_cast<float4 *>(a.samples_out + base)[tid] = make_float4(f[0], f[1], f[2], f[3]);
+    else
+      for (uint32_t j = 0; j < 4; j++)
+        if (i + j < here)
+          a.samples_out[base + i + j] = f[j];
+    __syncthreads();
+  }
+}
+
+// ---- A-XDR, value size 24 (the other size the configs name): four samples are exactly three words, so a thread turns
+// one 128-bit load into three word stores (the 32 threads of a warp write 384 contiguous bytes) and back; no shared
+// memory, no barrier, same structure as the value-size-32 kernels.
+__global__ void __launch_bounds__(256) axdr_encode24_kernel(const AxdrArgs a, const uint32_t total_quads)
+{
+  const float lo_bound = -8388608.0f, hi_bound = 8388607.0f;   // -(float)2^23, (float)(2^23 - 1): normalize.c:21-22
+  const float4 *in = reinterpret_cast<const float4 *>(a.samples_in);
+  const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x, gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t s = gtid; s < a.n_streams; s += gsize)   // the index: equal records
+  {
+    a.bit_len[s] = a.len * 24;
+    a.byte_off[s] = s * a.words_per_stream * 4ull;
+  }
+  if (gtid == 0)
+    a.byte_off[a.n_streams] = a.n_streams * a.words_per_stream * 4ull;
+  for (uint32_t q = (uint32_t)gtid; q < total_quads; q += (uint32_t)gsize)
+  {
+    const float4 v = __ldg(in + q);
+    uint32_t n0, n1, n2, n3;
+    const bool ok0 = normalize_small(v.x, a.nf, lo_bound, hi_bound, n0), ok1 = normalize_small(v.y, a.nf, lo_bound, hi_bound, n1);
+    const bool ok2 = normalize_small(v.z, a.nf, lo_bound, hi_bound, n2), ok3 = normalize_small(v.w, a.nf, lo_bound, hi_bound, n3);
+    n0 &= 0xFFFFFFu; n1 &= 0xFFFFFFu; n2 &= 0xFFFFFFu; n3 &= 0xFFFFFFu;
+    uint32_t *out = a.payload_words + 3ull * q;
+    out[0] = bswap32((n0 << 8) | (n1 >> 16));
+    out[1] = bswap32((n1 << 16) | (n2 >> 8));
+    out[2] = bswap32((n2 << 24) | n3);
+    if (!(ok0 && ok1 && ok2 && ok3))   // rare: remember which stream, the caller redoes the batch on the general path
+    {
+      const bool okj[4] = { ok0, ok1, ok2, ok3 };
+      for (uint32_t j = 0; j < 4; j++)
+        if (!okj[j])
+          a.status[(4ull * q + j) / a.len] = DC_ERR_INVALID_VALUE_D;
+      atomicExch(a.err_flag, 1ull);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) axdr_decode24_kernel(const AxdrArgs a, const uint32_t total_quads)
+{
+  const uint32_t *in = reinterpret_cast<const uint32_t *>(a.payload);
+  float4 *out = reinterpret_cast<float4 *>(a.samples_out);
+  const float nf = a.nf;
+  const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x, gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t s = gtid; s < a.n_streams; s += gsize)
+  {
+    a.n_out[s] = a.len;
+    a.status[s] = 0;
+  }
+  for (uint32_t q = (uint32_t)gtid; q < total_quads; q += (uint32_t)gsize)
+  {
+    const uint32_t *w = in + 3ull * q;
+    const uint32_t w0 = bswap32(__ldg(w)), w1 = bswap32(__ldg(w + 1)), w2 = bswap32(__ldg(w + 2));
+    // four 24-bit fields, sign-extended (EXTEND_IO_INT_SIGN, io_macros.h:89-90): shift the field to the top, then down again
+    const int32_t v0 = (int32_t)w0 >> 8;
+    const int32_t v1 = (int32_t)((w0 << 24) | (w1 >> 8)) >> 8;
+    const int32_t v2 = (int32_t)((w1 << 16) | (w2 >> 16)) >> 8;
+    const int32_t v3 = (int32_t)(w2 << 8) >> 8;
+    float4 f;   // normalize.c:36-39
+    f.x = __fdiv_rn(__int2float_rn(v0), nf);
+    f.y = __fdiv_rn(__int2float_rn(v1), nf);
+    f.z = __fdiv_rn(__int2float_rn(v2), nf);
+    f.w = __fdiv_rn(__int2float_rn(v3), nf);
+    out[q] = f;
+  }
+}
+
 void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
 {
   const uint64_t total = (a.n_streams * a.words_per_stream + 3) / 4;
@@ -428,7 +624,14 @@ void launch_axdr_encode(const AxdrArgs &a, cudaStream_t st)
   const uint64_t cap = (uint64_t)sm_count() * 16;                                // grid-stride over a multiple of the SM count
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const uint64_t total_words = a.n_streams * a.words_per_stream;
-  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.payload_words) & 15) == 0 &&
+  if (a.vs == 24 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0 && (a.n_streams * a.len) % 4 == 0 && a.n_streams * a.len < (1ull << 33))
+    axdr_encode24_kernel<<<grid, block, 0, st>>>(a, (uint32_t)(a.n_streams * a.len / 4));
+  else if (a.vs < 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0)
+  {
+    const uint64_t total_samples = a.n_streams * a.len, tiles = (total_samples + kAxdrTile - 1) / kAxdrTile;
+    axdr_encode_tiled_kernel<<<(unsigned)(tiles < cap ? tiles : cap), block, 0, st>>>(a, total_samples);
+  }
+  else if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.payload_words) & 15) == 0 &&
       a.words_per_stream >= 4 && total_words % 4 == 0 && total_words < (1ull << 32))
     axdr_encode32_kernel<<<grid, block, 0, st>>>(a, make_magic32((uint32_t)a.words_per_stream), (uint32_t)(total_words / 4));
   else if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.samples_in) & 15) == 0)
@@ -448,7 +651,14 @@ void launch_axdr_decode(const AxdrArgs &a, cudaStream_t st)
   const uint64_t cap = (uint64_t)sm_count() * 16;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const uint64_t total_samples = a.n_streams * a.len;
-  if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.payload) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0 &&
+  if (a.vs == 24 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0 && total_samples % 4 == 0 && total_samples < (1ull << 33))
+    axdr_decode24_kernel<<<grid, block, 0, st>>>(a, (uint32_t)(total_samples / 4));
+  else if (a.vs < 32 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0)
+  {
+    const uint64_t tiles = (total_samples + kAxdrTile - 1) / kAxdrTile;
+    axdr_decode_tiled_kernel<<<(unsigned)(tiles < cap ? tiles : cap), block, 0, st>>>(a, total_samples);
+  }
+  else if (a.vs == 32 && (reinterpret_cast<uintptr_t>(a.payload) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.samples_out) & 15) == 0 &&
       a.len >= 4 && total_samples % 4 == 0 && total_samples < (1ull << 32))
     axdr_decode32_kernel<<<grid, block, 0, st>>>(a, make_magic32((uint32_t)a.len), (uint32_t)(total_samples / 4));
   else
