@@ -94,7 +94,7 @@ def test_n_rank_container_written_from_gpu_encodes_decodes_back(tmp_path, oracle
     per = -(-CHANNEL_LEN // BLOCK_LEN)
     assert all(r[1] for r in res), [r[5] for r in res]
     assert all(r[3] == N_CHANNELS * per for r in res)
-    assert sum(r[2]["sizes"]) == res[0][4] and res[0][2]["byte_base"] == 0
+    assert sum(res[0][2]["sizes"]) == res[0][4] and res[0][2]["byte_base"] == 0
     # the common file holds, stream by stream, what the oracle (= the reference's DCCLI) writes
     from data_compressor_b200 import container as ct, synth
     x_all = synth.redd_like(N_CHANNELS, CHANNEL_LEN, device="cpu", seed=0xC0FFEE).numpy()
