@@ -959,10 +959,26 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *scratch, uin
   const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src);
   uint32_t *dst_w = reinterpret_cast<uint32_t *>(dst + head);
   const uint32_t sh = (uint32_t)head * 8;   // source words are read shifted by `head` bytes (little-endian memory)
-  for (uint64_t k = lane; k < nwords; k += 32)
+  // four trips' loads first, then the stores: the copy is latency bound (a warp moves ~1.6 KB), so what counts is how many
+  // loads a lane has in flight
+  uint64_t k = lane;
+  for (; k + 96 < nwords; k += 128)
   {
-    const uint32_t a = src_w[k];
-    const uint32_t v = sh ? __funnelshift_r(a, src_w[k + 1], sh) : a;
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      a[j] = __ldg(src_w + k + 32 * j);
+      b[j] = sh ? __ldg(src_w + k + 32 * j + 1) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      dst_w[k + 32 * j] = sh ? __funnelshift_r(a[j], b[j], sh) : a[j];
+  }
+  for (; k < nwords; k += 32)
+  {
+    const uint32_t a = __ldg(src_w + k);
+    const uint32_t v = sh ? __funnelshift_r(a, __ldg(src_w + k + 1), sh) : a;
     dst_w[k] = v;
   }
   const uint64_t done = head + nwords * 4;

@@ -188,6 +188,30 @@ def test_batch_value_sizes(ctx, oracle, vs):
     assert torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32))
 
 
+def test_batch_streams_with_long_code_words(ctx, oracle):
+    """Deltas of 2^15 and more (SEG code words of 33 .. 63 bits: appliances switching) between short ones, at every
+    value size the specialised back end takes; the decoder's medium path and the general parser must agree with the oracle."""
+    rng = np.random.default_rng(71)
+    nc, cl = 40, 700
+    k = np.abs(np.cumsum(rng.integers(-200, 201, (nc, cl)), axis=1) + 30000)
+    jumps = rng.random((nc, cl)) < 0.03
+    k = np.abs(k + np.cumsum(np.where(jumps, rng.integers(-1_000_000, 1_000_001, (nc, cl)), 0), axis=1)) % (1 << 21)   # float32 round trip stays exact (SURVEY a-2)
+    x = (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
+    for vs in (25, 32, 40):
+        enc = ctx.dega_encode(torch.from_numpy(x).cuda(), block_len=175, vs=vs)
+        assert not enc.status.any().item()
+        for s, xs in enumerate(split_streams(x, 175)):
+            if s % 7 == 0:
+                assert enc.stream_bytes(s) == oracle.dega_encode(xs, vs=vs)[1], (vs, s)
+        y, n_out, status = ctx.dega_decode(enc, vs=vs)
+        assert not status.any().item() and torch.equal(y.view(torch.int32).cpu(), torch.from_numpy(x).view(torch.int32)), vs
+        # the decoder against the oracle's decoder on the same payload (not only a round trip)
+        for s in (0, 33, 159):
+            pay = enc.stream_bytes(s)
+            rc, want = oracle.dega_decode(pay, int(enc.bit_len[s]), vs=vs)
+            assert rc == 0 and np.array_equal(want.view(np.uint32), y.cpu().numpy().reshape(-1, 175)[s].view(np.uint32))
+
+
 def test_batch_failed_streams_are_isolated(ctx, oracle):
     x = np.full((4, 50), 12.5, dtype=np.float32)
     x[1, 20] = -3.0            # diff rejects (SURVEY.md a-3)

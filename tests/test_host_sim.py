@@ -47,6 +47,9 @@ def test_random_streams_vs_oracle(sim, oracle, seed):
     rng = np.random.default_rng(seed)
     n = int(rng.integers(0, 3000))
     k = np.abs(np.cumsum(rng.integers(-int(rng.choice([3, 300, 30000])), 301, n)) + 20000)
+    if seed % 2:   # appliance-like jumps: code words of 33 bits and more (|delta| >= 2^15) between the short ones
+        jumps = rng.random(n) < 0.02
+        k = np.abs(k + np.cumsum(np.where(jumps, rng.integers(-3_000_000, 3_000_001, n), 0))) % (1 << 20)   # fits every value size drawn below
     x = (k.astype(np.float32) / np.float32(100.0)).astype(np.float32)
     vs = int(rng.choice([22, 24, 32, 33, 48, 64]))
     ad = int(rng.integers(0, 2))
