@@ -323,6 +323,7 @@ def run_ours(args):
     barrier()
     launches0 = ctx.launch_count()
     kernel_ms = {}
+    pendings = []
     t_enc = t_dec = 0.0
     with torch.cuda.stream(ctx.stream):
         ev0.record(ctx.stream)
@@ -330,14 +331,14 @@ def run_ours(args):
         for it in range(args.steps):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
-            pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
+            if world > 1:   # started now, resolved when the offsets are needed (here: before the timed region ends)
+                pendings.append(shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev))
             ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
             km2 = ctx.kernel_ms()
-            if pending is not None:
-                sizes = pending.result()   # container offsets of this rank: inside the timed step, off its critical path
             for k, v in list(km.items()) + list(km2.items()):
                 kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             step_ev[it + 1].record(ctx.stream)
+        sizes = [p_.result() for p_ in pendings]   # every step's container offsets: inside the timed region, off the steps' critical path
         ev1.record(ctx.stream)
     barrier()
     launches = ctx.launch_count() - launches0
