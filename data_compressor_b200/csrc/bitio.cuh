@@ -245,6 +245,69 @@ struct BitReader
   }
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Reader of the arithmetic decoder: one stream of a dense payload (any byte address, the next stream right behind it),
+// positions in 32 bits, the word after the current one always in hand (`pre`), so that a refill is one predicated load,
+// one byte swap and one funnel shift.  Bits past the end read as zero (bac.c:173-183); the caller keeps counting them in
+// `pos` and decides when that is an error.  Only what the decoder uses: a 64-bit MSB-aligned window `win` holding `wn`
+// bits, refill() when 32 or fewer are left.
+struct DenseReader
+{
+  const uint32_t *words;   // 4-byte aligned base
+  uint32_t phase;          // 0, 8, 16, 24: bit offset of the stream inside words[0]
+  uint32_t span;           // aligned words the stream touches
+  uint32_t end;            // phase + nbits: the stream's end, in bits from words[0]
+  uint32_t next;           // aligned word `pre` does not hold yet
+  uint32_t carry;          // BE(words[next - 1]) (or 0 past the end)
+  uint32_t pre;            // stream bits [32 k, 32 k + 32) for the next refill
+  uint32_t k;              // index of the chunk in `pre`
+  uint64_t win;
+  uint32_t wn;
+  uint32_t pos;            // bits consumed, counted past the end too
+
+  __device__ __forceinline__ uint32_t aligned(uint32_t i) const { return i < span ? bswap32(__ldg(words + i)) : 0u; }
+
+  // chunk k of the stream = bits [phase + 32 k, phase + 32 k + 32) of the aligned words, zero past the stream's end
+  __device__ __forceinline__ uint32_t chunk()
+  {
+    const uint32_t nx = aligned(next);
+    uint32_t w = __funnelshift_l(nx, carry, phase);   // phase == 0: carry itself
+    carry = nx;
+    next++;
+    const uint32_t first = phase + 32 * k;            // position of the chunk's first bit
+    if (first + 32 > end)                             // the stream ends inside (or before) this chunk: once per stream
+      w = first >= end ? 0u : w & ~(0xFFFFFFFFu >> (end - first));
+    k++;
+    return w;
+  }
+
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t nbits)
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    phase = (uint32_t)(a & 3) * 8;
+    end = phase + nbits;
+    span = (end + 31) >> 5;
+    carry = aligned(0);
+    next = 1;
+    k = 0;
+    win = 0;
+    wn = 0;
+    pos = 0;
+    pre = chunk();
+  }
+
+  __device__ __forceinline__ void refill()
+  {
+    if (wn <= 32)
+    {
+      win |= (uint64_t)pre << (32 - wn);
+      wn += 32;
+      pre = chunk();
+    }
+  }
+};
+
 __device__ __forceinline__ const uint8_t *src_ptr(const BitSrc &s, uint64_t i)
 {
   if (s.interleave)
