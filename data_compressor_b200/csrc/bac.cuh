@@ -58,6 +58,18 @@ __device__ __forceinline__ uint32_t clz_nz(uint32_t a)
 }
 #endif
 
+// Position of the leading one, 0xFFFFFFFF (-1) for zero: bfind.u32 is a single FLO.U32
+#ifdef DC_HOST_SIM
+static inline uint32_t bfind_u32(uint32_t a) { return a ? 31u - (uint32_t)__builtin_clz(a) : 0xFFFFFFFFu; }
+#else
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t a)
+{
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
+#endif
+
 // shift that goes with DivEntry::m of divisor d >= 3: ceil(log2 d) - 2
 __device__ __forceinline__ uint32_t div_shift(uint32_t d) { return 30u - clz_nz(d - 1u); }
 // floor(x / d) for x < 2^30 with the table entry of d and sh = div_shift(d)
@@ -468,6 +480,28 @@ struct BacEncoder
     rng = r1 << n;
     a0 = __funnelshift_l(LO0, (uint32_t)(x >> 32), n);
     LO = LO0 << n;
+  }
+
+  // The unrolled groups of the encoder keep the interval in ONE register W instead of (a0, LO): bit 0 a guard (zero in
+  // W, one in the high end), bits 16..1 the 16-bit window, bits 31..17 the bits that left the window since they were last
+  // taken out -- the carry of lo += dlo runs into them by itself and a doubling is one shift.  That costs a 1-cycle add
+  // and a shift per symbol where (a0, LO) takes a 64-bit multiply-add and a funnel shift; the price is room for only 14
+  // bits (plus the carry), so the caller takes the bits out every half group and checks the counts afterwards.
+  //   H = 2 hi + 1; first differing bit b = leading one of (W ^ H) & 0x1FFFF (the guards differ: never zero);
+  //   u = (~W | H) below b; its leading one q (-1: none, lo == hi) is the first bit under the E3 run, n = 15 - q.
+  // q is in [-1, 15] for ANY input, so a group that lost bits cannot produce a wild shift count.
+  static __device__ __forceinline__ uint32_t to_w(uint32_t LO) { return LO >> 15; }
+  static __device__ __forceinline__ uint32_t from_w(uint32_t W) { return W << 15; }
+  __device__ __forceinline__ void narrow_w(uint32_t &W, uint32_t dlo, uint32_t r1, uint32_t &qsum)
+  {
+    W += dlo << 1;
+    const uint32_t H = W + (r1 << 1) - 1u;
+    const uint32_t cz = clz_nz((W ^ H) & 0x1FFFFu);
+    const uint32_t q = bfind_u32((~W | H) & (0x7FFFFFFFu >> cz));
+    const uint32_t n = 15u - q;
+    qsum += q;
+    rng = r1 << n;
+    W <<= n;
   }
 
   // EncodeSymbol for a data bit (bac.c:107-111); c1m1 = cum[1] - 1
