@@ -516,7 +516,7 @@ def run_ours(args):
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu capture, only valid for the shape it was taken on
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if tj["workload"] == {"channels": C_, "samples": S_, "block_len": L_}:
             traffic = tj.get(dom + "_kernel")
     except Exception:
@@ -530,15 +530,15 @@ def run_ours(args):
             peak_i = 4 * sms * mhz * 1e6 / 1e9
             issue = {"achieved": wi / (dom_ms * 1e-3) / 1e9, "peak": peak_i, "unit": "G warp instructions/s", "frac": wi / (dom_ms * 1e-3) / 1e9 / peak_i,
                      "warp_instructions_per_launch": wi, "note": "peak = 4 schedulers x SMs x sampled SM clock, one instruction per cycle; IMAD / LOP3 / SHF / SEL occupy "
-                     "their pipe for 2 cycles each on this part and do not overlap each other (profiles/r1_ubench_pipes.txt: 0.53 per cycle for such "
-                     "a mix), plain adds and predicate logic take 1"}
+                     "their pipe for 2 cycles each on this part (IMAD.HI 4) and the kernels load the ALU pipe and the heavy FMA pipe about "
+                     "equally (profiles/r2_ubench_pipes.txt, profiles/r2_coder_experiments.txt); plain adds and predicate logic take 1"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "issue_bound": issue, "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": dom_ms,
-                "note": "the coder is sequential per stream and bound by integer instruction issue (~1.9 cycles per integer instruction per scheduler, profiles/r1_ubench_pipes.txt; DRAM < 4 %): "
-                        "DESIGN.md 3.1, profiles/r1h_dega_ncu_summary.txt"}
+                "note": "the coder is sequential per stream and bound by integer instruction issue (1 to 2 cycles per integer instruction per scheduler, profiles/r2_ubench_pipes.txt; DRAM < 4 %): "
+                        "DESIGN.md 3.1, profiles/r2d_dega_ncu_summary.txt"}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cpu = None
