@@ -286,10 +286,11 @@ def run_ours(args):
 
     def step():
         e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
-        # the only collective on the path: per-shard payload byte counts -> container offsets (16 B per rank).  It is
-        # started here and resolved after the decode: nothing in the decode needs the other ranks' sizes
-        pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
+        # the only collective on the path: per-shard payload byte counts -> container offsets (16 B per rank).  Nothing in
+        # the decode needs the other ranks' sizes: the decode is queued first, the exchange is started behind it (its host
+        # side then runs while the GPU decodes) and resolved afterwards
         ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+        pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
         if pending is not None:
             pending.result()
         return e
@@ -331,14 +332,14 @@ def run_ours(args):
         for it in range(args.steps):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
-            if world > 1:   # started now, resolved when the offsets are needed (here: before the timed region ends)
-                pendings.append(shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev))
             ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+            if world > 1:   # started behind the queued decode, resolved when the offsets are needed (here: before the timed region ends)
+                pendings.append(shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev))
             km2 = ctx.kernel_ms()
             for k, v in list(km.items()) + list(km2.items()):
                 kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             step_ev[it + 1].record(ctx.stream)
-        sizes = [p_.result() for p_ in pendings]   # every step's container offsets: inside the timed region, off the steps' critical path
+        sizes = shard.resolve_all(pendings)   # every step's container offsets: inside the timed region, off the steps' critical path, one copy back
         ev1.record(ctx.stream)
     barrier()
     launches = ctx.launch_count() - launches0

@@ -46,16 +46,30 @@ class PendingSizes:
     def __init__(self, rank, world, gathered, work):
         self.rank, self.world, self.gathered, self.work = rank, world, gathered, work
 
-    def result(self) -> dict:
-        if self.work is not None:
-            self.work.wait()
-        allv = self.gathered.view(self.world, 2).cpu()
+    def _dict(self, allv) -> dict:
         sizes, counts = allv[:, 0].tolist(), allv[:, 1].tolist()
         return {
             "rank": self.rank, "world": self.world, "sizes": sizes, "counts": counts,
             "byte_base": sum(sizes[:self.rank]), "stream_base": sum(counts[:self.rank]),
             "total_bytes": sum(sizes), "total_streams": sum(counts),
         }
+
+    def result(self) -> dict:
+        if self.work is not None:
+            self.work.wait()
+        return self._dict(self.gathered.view(self.world, 2).cpu())
+
+
+def resolve_all(pendings) -> list:
+    """result() of several exchanges with ONE device-to-host copy (a batch of jobs whose containers are written together)."""
+    pendings = list(pendings)
+    if not pendings:
+        return []
+    for p in pendings:
+        if p.work is not None:
+            p.work.wait()
+    allv = torch.stack([p.gathered.view(p.world, 2) for p in pendings]).cpu()
+    return [p._dict(allv[i]) for i, p in enumerate(pendings)]
 
 
 def exchange_sizes_async(total_bytes: int, n_streams: int, device, group=None) -> PendingSizes:

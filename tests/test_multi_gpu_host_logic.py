@@ -40,6 +40,11 @@ def _worker(rank, world, port, n_channels, block_len, q, container_path=None):
     local_off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64)
     info = shard.exchange_sizes(len(payload), len(sizes), torch.device("cpu"))
     goff = shard.global_byte_offsets(local_off, info["byte_base"])
+    # the deferred forms give the same dictionaries: one at a time, and several jobs resolved with one copy back
+    pend = [shard.exchange_sizes_async(len(payload) + k, len(sizes), torch.device("cpu")) for k in range(3)]
+    assert pend[0].result() == info
+    many = shard.resolve_all(pend)
+    assert many[0] == info and [m["sizes"][rank] for m in many] == [len(payload) + k for k in range(3)]
     if container_path is not None:
         # every rank writes its own slice of ONE file: rank 0 creates it, a barrier, then position-based writes
         from data_compressor_b200 import container as ct
