@@ -286,11 +286,13 @@ def run_ours(args):
 
     def step():
         e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
-        # the only collective on the path: per-shard payload byte counts -> container offsets (16 B per rank).  Nothing in
-        # the decode needs the other ranks' sizes: the decode is queued first, the exchange is started behind it (its host
-        # side then runs while the GPU decodes) and resolved afterwards
-        ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
+        # the only collective on the path: per-shard payload byte counts -> container offsets (16 B per rank).  It is
+        # started here, while the GPU is between the two passes, and resolved after the decode: nothing in the decode needs
+        # the other ranks' sizes.  Measured side by side on two GPUs (profiles/ubench/xchg_variants.sh): this order 12.74 ms a
+        # step, the decode queued first and the collective behind it 12.98 (its kernel then waits for room behind the resident
+        # decoder grid), the collective on a stream of its own from preallocated pinned slots 13.1-13.7.
         pending = shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev) if world > 1 else None
+        ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
         if pending is not None:
             pending.result()
         return e
@@ -332,14 +334,14 @@ def run_ours(args):
         for it in range(args.steps):
             e = ctx.dega_encode(x, block_len=L_, vs=VS, nf=NF, adaptive=ADAPTIVE, out=enc)
             km = ctx.kernel_ms()
-            ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
-            if world > 1:   # started behind the queued decode, resolved when the offsets are needed (here: before the timed region ends)
+            if world > 1:   # started now, resolved when the offsets are needed (here: before the timed region ends)
                 pendings.append(shard.exchange_sizes_async(e.total_bytes, e.n_streams, dev))
+            ctx.dega_decode(e, vs=VS, nf=NF, adaptive=ADAPTIVE, out=y)
             km2 = ctx.kernel_ms()
             for k, v in list(km.items()) + list(km2.items()):
                 kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             step_ev[it + 1].record(ctx.stream)
-        sizes = shard.resolve_all(pendings)   # every step's container offsets: inside the timed region, off the steps' critical path, one copy back
+        sizes = shard.resolve_all(pendings)   # every step's container offsets: inside the timed region, off the steps' critical path
         ev1.record(ctx.stream)
     barrier()
     launches = ctx.launch_count() - launches0
