@@ -705,7 +705,10 @@ void launch_aggregate(const float *in, uint64_t n_channels, uint64_t channel_len
 // Arithmetic coder kernels.  The 128 KiB division table lives in shared memory (one copy per CTA, one CTA of
 // kBacThreads threads per SM); before the first halving every lane of a warp has coded the same number of
 // symbols, so `total` is warp-uniform and the table read is a broadcast.
-static const int kBacThreads = 1024;
+#ifndef DC_BAC_THREADS
+#define DC_BAC_THREADS 1024
+#endif
+static const int kBacThreads = DC_BAC_THREADS;
 
 int bac_smem_bytes() { return kDivTableEntries * (int)sizeof(DivEntry); }
 int bac_threads_per_sm() { return kBacThreads; }
