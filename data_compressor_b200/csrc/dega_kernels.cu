@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(128) back_kernel(const BackArgs a)
 #ifndef BACK_MIN_CTAS
 #define BACK_MIN_CTAS 12
 #endif
-template <int MODE>
-__global__ void __launch_bounds__(128, BACK_MIN_CTAS) back_dega_kernel(const BackArgs a)
+// CTAS: what the build is for.  BACK_MIN_CTAS gets 40 registers; 8 gets 48 and is 4 % faster where 10 or fewer CTAs per SM are
+// wanted anyway (launch_back picks the count by the shape of the job).
+template <int MODE, int CTAS = BACK_MIN_CTAS>
+__global__ void __launch_bounds__(128, CTAS) back_dega_kernel(const BackArgs a)
 {
   __shared__ float stage[128 * kBackStage];   // decoded samples per thread, leaving as 128-bit stores of whole sectors
   float *mine = stage + threadIdx.x * kBackStage;
@@ -133,9 +135,26 @@ void launch_back(const BackArgs &a, cudaStream_t st)
       (reinterpret_cast<uintptr_t>(a.in.base) & 3) == 0)
   {
     cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st);
-    const unsigned rgrid = resident_grid(a.n_streams, block, BACK_MIN_CTAS);
+    // How many CTAs per SM: the kernel is built for BACK_MIN_CTAS, and from 8 up its throughput hardly depends on the
+    // number, but a last round that is a third full does cost (303 104 streams: 1.15 ms at 12 CTAs per SM = 1.33 rounds,
+    // 1.05 ms at 8 = 2 rounds; 348 160 streams: 10 = 1.84 rounds).  So: the count whose rounds waste the fewest thread slots, the larger one on a tie.
+    unsigned ctas = BACK_MIN_CTAS;
+    uint64_t best = ~0ull;
+    for (unsigned c = BACK_MIN_CTAS; c >= 8; c--)
+    {
+      const uint64_t per_round = (uint64_t)sm_count() * c * block;
+      const uint64_t slots = (a.n_streams + per_round - 1) / per_round * c;
+      if (slots < best)
+      {
+        best = slots;
+        ctas = c;
+      }
+    }
+    const unsigned rgrid = resident_grid(a.n_streams, block, ctas);
     const bool narrow = a.vs <= 32 && a.in.stride_bytes < (1ull << 28);   // every stream shorter than 2^31 bits
-    if (narrow && a.vs == 32 && a.in.interleave)
+    if (narrow && a.vs == 32 && a.in.interleave && ctas <= 10)
+      back_dega_kernel<2, 8><<<rgrid, block, 0, st>>>(a);
+    else if (narrow && a.vs == 32 && a.in.interleave)
       back_dega_kernel<2><<<rgrid, block, 0, st>>>(a);
     else if (narrow)
       back_dega_kernel<1><<<rgrid, block, 0, st>>>(a);
