@@ -1,3 +1,7 @@
+# Size-exchange variants on two GPUs, side by side on one box.  DC_XCHG / DC_ORDER / DC_RESOLVE were temporary switches
+# patched into bench.py and shard.py for this run only (simple = the tree's exchange_sizes_async, ring = preallocated pinned slots on a side stream;
+# first / after = collective started before / after the decode is queued; each / all = results fetched one by one / stacked on the device).
+# The tree keeps what won: simple, first, each.
 mkdir -p gpurun_out/mg
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu --no-e2e --no-extra"
 for rep in 1 2; do
