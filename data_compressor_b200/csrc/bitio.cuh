@@ -246,64 +246,58 @@ struct BitReader
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Reader of the arithmetic decoder: one stream of a dense payload (any byte address, the next stream right behind it),
-// positions in 32 bits, the word after the current one always in hand (`pre`), so that a refill is one predicated load,
-// one byte swap and one funnel shift.  Bits past the end read as zero (bac.c:173-183); the caller keeps counting them in
-// `pos` and decides when that is an error.  Only what the decoder uses: a 64-bit MSB-aligned window `win` holding `wn`
-// bits, refill() when 32 or fewer are left.
+// Reader of the arithmetic decoder: one stream of a dense payload (any byte address, the next stream right behind it).
+// Only what the decoder uses: "the 32 bits at the current position" and "move on by up to 32 bits", positions in 32 bits.
+// Two consecutive aligned words of the payload are held (byte order undone, bits past the stream's end cleared when the
+// word is loaded) with the number of bits of the first that are used up: a peek is one funnel shift, moving on an add and,
+// when the first word is used up, one predicated load and byte swap.  Bits past the end read as zero (bac.c:173-183); the
+// caller keeps counting them in `pos` and decides when that is an error.
 struct DenseReader
 {
   const uint32_t *words;   // 4-byte aligned base
-  uint32_t phase;          // 0, 8, 16, 24: bit offset of the stream inside words[0]
   uint32_t span;           // aligned words the stream touches
-  uint32_t end;            // phase + nbits: the stream's end, in bits from words[0]
-  uint32_t next;           // aligned word `pre` does not hold yet
-  uint32_t carry;          // BE(words[next - 1]) (or 0 past the end)
-  uint32_t pre;            // stream bits [32 k, 32 k + 32) for the next refill
-  uint32_t k;              // index of the chunk in `pre`
-  uint64_t win;
-  uint32_t wn;
+  uint32_t endmask;        // the stream's bits in the last of them
+  uint32_t idx;            // index of the aligned word in `nxt`
+  uint32_t cur, nxt;
+  uint32_t off;            // bits of `cur` used up: 0..31 between calls (starts at the stream's byte phase)
   uint32_t pos;            // bits consumed, counted past the end too
 
-  __device__ __forceinline__ uint32_t aligned(uint32_t i) const { return i < span ? bswap32(__ldg(words + i)) : 0u; }
-
-  // chunk k of the stream = bits [phase + 32 k, phase + 32 k + 32) of the aligned words, zero past the stream's end
-  __device__ __forceinline__ uint32_t chunk()
+  __device__ __forceinline__ uint32_t aligned(uint32_t i) const
   {
-    const uint32_t nx = aligned(next);
-    uint32_t w = __funnelshift_l(nx, carry, phase);   // phase == 0: carry itself
-    carry = nx;
-    next++;
-    const uint32_t first = phase + 32 * k;            // position of the chunk's first bit
-    if (first + 32 > end)                             // the stream ends inside (or before) this chunk: once per stream
-      w = first >= end ? 0u : w & ~(0xFFFFFFFFu >> (end - first));
-    k++;
-    return w;
+    if (i >= span)
+      return 0u;
+    const uint32_t w = bswap32(__ldg(words + i));
+    return i + 1 == span ? w & endmask : w;
   }
 
   __device__ __forceinline__ void init(const uint8_t *p, uint32_t nbits)
   {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    phase = (uint32_t)(a & 3) * 8;
-    end = phase + nbits;
+    off = (uint32_t)(a & 3) * 8;
+    const uint32_t end = off + nbits;   // the stream's end, in bits from words[0]
     span = (end + 31) >> 5;
-    carry = aligned(0);
-    next = 1;
-    k = 0;
-    win = 0;
-    wn = 0;
+    endmask = (end & 31) ? ~(0xFFFFFFFFu >> (end & 31)) : 0xFFFFFFFFu;
+    cur = aligned(0);
+    nxt = aligned(1);
+    idx = 1;
     pos = 0;
-    pre = chunk();
   }
 
-  __device__ __forceinline__ void refill()
+  // the next 32 bits of the stream
+  __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(nxt, cur, off); }
+
+  // n <= 32
+  __device__ __forceinline__ void advance(uint32_t n)
   {
-    if (wn <= 32)
+    off += n;
+    pos += n;
+    if (off >= 32)
     {
-      win |= (uint64_t)pre << (32 - wn);
-      wn += 32;
-      pre = chunk();
+      off -= 32;
+      cur = nxt;
+      idx++;
+      nxt = aligned(idx);
     }
   }
 };
