@@ -86,6 +86,14 @@ struct BitWriter
       flush_word();
   }
 
+  // a whole word at a word boundary (nacc == 0): no trip through the accumulator
+  __device__ __forceinline__ void put_word(uint32_t v)
+  {
+    if (nwords < cap_words)
+      words[(uint64_t)nwords * wstride] = bswap32(v);
+    nwords++;
+  }
+
   // n in [0, 64], v < 2^n
   __device__ __forceinline__ void put64(uint64_t v, uint32_t n)
   {
