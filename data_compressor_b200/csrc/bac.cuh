@@ -370,7 +370,7 @@ struct CarryWriter
   uint32_t cap_words;
   uint32_t nwords;
   uint32_t nacc;      // < 32 between calls
-  uint64_t acc;
+  uint32_t acc;       // the nacc bits not stored yet, and at bit nacc a carry that still has to reach what was stored before
   bool overflow;      // valid after finish()
 
   __device__ __forceinline__ void init(uint8_t *p, uint64_t cap_bytes)
@@ -389,26 +389,28 @@ struct CarryWriter
       bac_ripple(words, nwords);
   }
 
-  __device__ __forceinline__ void flush_word()   // requires 32 <= nacc <= 63
-  {
-    const uint32_t k = nacc - 32;
-    const uint64_t t = acc >> k;                 // 32 bits to store + the carry bit
-    acc &= ~(~0ull << k);
-    nacc = k;
-    if ((uint32_t)(t >> 32))
-      ripple();
-    if (nwords < cap_words)
-      words[nwords] = bswap32((uint32_t)t);
-    nwords++;
-  }
-
   // appends the low k bits of v (k <= 31); bit k of v, if set, is a carry into the bits appended earlier
   __device__ __forceinline__ void push(uint32_t v, uint32_t k)
   {
-    acc = (acc << k) + v;
-    nacc += k;
-    if (nacc >= 32)
-      flush_word();
+    const uint64_t c = ((uint64_t)acc << k) + v;   // at most 62 bits and the carry above them
+    const uint32_t tot = nacc + k;
+    if (tot >= 32)
+    {
+      const uint32_t r = tot - 32;                 // bits that stay behind: 0..30
+      const uint64_t t = c >> r;                   // 32 bits to store + the carry bit
+      acc = (uint32_t)c & ~(0xFFFFFFFFu << r);
+      nacc = r;
+      if ((uint32_t)(t >> 32))
+        ripple();
+      if (nwords < cap_words)
+        words[nwords] = bswap32((uint32_t)t);
+      nwords++;
+    }
+    else
+    {
+      acc = (uint32_t)c;                           // fits: tot bits and the carry at bit tot <= 31
+      nacc = tot;
+    }
   }
 
   __device__ __forceinline__ uint64_t bits() const { return (uint64_t)nwords * 32 + nacc; }
@@ -416,15 +418,15 @@ struct CarryWriter
   // resolves a carry that is still waiting, stores the fractional word (left aligned, zero padded)
   __device__ __forceinline__ uint64_t finish()
   {
-    if ((uint32_t)(acc >> nacc))
+    if (acc >> nacc)
     {
       ripple();
-      acc &= ~(~0ull << nacc);
+      acc &= ~(0xFFFFFFFFu << nacc);
     }
     const uint64_t total = bits();
     overflow = nwords + (nacc ? 1u : 0u) > cap_words;
     if (nacc && nwords < cap_words)
-      words[nwords] = bswap32((uint32_t)acc << (32 - nacc));
+      words[nwords] = bswap32(acc << (32 - nacc));
     return total;
   }
 };
