@@ -57,6 +57,36 @@ uint64_t sim_csv_encode(const uint32_t *values, uint64_t n, uint32_t column, cha
   return pos;
 }
 
+// DenseReader on its own: the stream of `nbits` bits that starts `byte_off` bytes into buf (an allocation of buf_bytes,
+// a multiple of 4); after every step the 32 bits at the current position are recorded, then the position moves on by steps[i]
+// (<= 32).  Returns the position (bits consumed, counted past the end too).
+uint32_t sim_dense_reader(const uint8_t *buf, uint64_t buf_bytes, uint32_t byte_off, uint32_t nbits, const uint32_t *steps, uint32_t n_steps,
+                          uint32_t *peeks)
+{
+  std::vector<uint8_t> copy(buf, buf + buf_bytes);   // the reader reads whole aligned words: keep them inside a known allocation
+  dc::DenseReader r;
+  r.init(copy.data() + byte_off, nbits);
+  for (uint32_t i = 0; i < n_steps; i++)
+  {
+    peeks[i] = r.peek32();
+    r.advance(steps[i]);
+  }
+  return r.pos;
+}
+
+// CarryWriter on its own: pushes (v[i], k[i]) (k <= 31, bit k of v = a carry into what was appended before), then finish();
+// returns the number of bits, the words land in out (cap_bytes).
+uint64_t sim_carry_writer(const uint32_t *v, const uint32_t *k, uint32_t n, uint8_t *out, uint64_t cap_bytes, int *overflow)
+{
+  dc::CarryWriter w;
+  w.init(out, cap_bytes);
+  for (uint32_t i = 0; i < n; i++)
+    w.push(v[i], k[i]);
+  const uint64_t bits = w.finish();
+  *overflow = w.overflow ? 1 : 0;
+  return bits;
+}
+
 // how often the arithmetic coder's unrolled groups ran out of room and were redone (which = 0 encoder, 1 decoder)
 uint64_t sim_bac_redo_count(int which) { return g_bac_redo[which & 1]; }
 

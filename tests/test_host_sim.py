@@ -231,3 +231,70 @@ def test_csv_field_conversion_matches_strtof(sim, oracle):
     assert all(sim.csv_field(f)[1] for f in ("0x10", "inf", "nan", "12345678901234567890", "1e39", "1e-46", "0.1234567891"))
     assert not any(sim.csv_field(f)[1] for f in ("1.5", "123456789", "1e3", "-2.5E-3", "1e", "1p3", "", "abc", "1000e-3"))
     assert n_fast > 5000
+
+
+def test_dense_reader_matches_a_plain_bit_string(sim):
+    """The arithmetic decoder's reader (bitio.cuh: DenseReader): every byte phase, stream ends anywhere in a word, bits
+    past the end read as zero, the stream that follows in the payload is never seen."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        buf = rng.integers(0, 256, 64, dtype=np.uint8)          # neighbours are random bits, not zeros
+        byte_off = int(rng.integers(0, 8))
+        nbits = int(rng.integers(0, 8 * (48 - byte_off)))
+        allbits = np.unpackbits(buf)[8 * byte_off: 8 * byte_off + nbits]
+        steps = rng.integers(0, 33, 24, dtype=np.uint32)
+        if trial % 3 == 0:
+            steps[:] = 32
+        peeks = np.zeros(steps.size, dtype=np.uint32)
+        pos = sim.lib.sim_dense_reader(buf.ctypes.data, buf.size, byte_off, nbits, steps.ctypes.data, steps.size, peeks.ctypes.data)
+        at = 0
+        for i, st in enumerate(steps):
+            window = np.zeros(32, dtype=np.uint8)
+            have = allbits[at:at + 32]
+            window[:have.size] = have
+            want = int(np.packbits(window).view(">u4")[0])
+            assert int(peeks[i]) == want, (trial, i, byte_off, nbits, at)
+            at += int(st)
+        assert pos == at
+
+
+def test_carry_writer_is_big_integer_addition(sim):
+    """The encoder's output stage (bac.cuh: CarryWriter): appending k bits with a carry bit above them is
+    X = (X << k) + v on an arbitrarily long integer -- carries through bits still pending and through stored words.
+    The sequences are what a coder can produce: the number written so far is the leading bits of a fixed target T, or one
+    below them (the low end of a shrinking interval creeps up on T), so the bits in front of any position change at most
+    once, by +1 -- the writer's precondition."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        n = int(rng.integers(1, 60))
+        ks = rng.integers(0, 32, n).astype(np.uint32)
+        vs = np.zeros(n, dtype=np.uint32)
+        total = int(ks.sum())
+        if trial % 2:
+            T = int.from_bytes(rng.bytes(total // 8 + 1), "big") >> (8 - total % 8) if total else 0
+        else:   # long runs of zeros and ones in the target: a lag of one below it is a long run of ones, the carry ripples far
+            T = 0
+            for _ in range(total):
+                T = (T << 1) | (1 if (T & 1 and rng.random() < 0.95) or (not T & 1 and rng.random() < 0.05) else 0)
+        T &= (1 << total) - 1 if total else 0
+        X, L, lag = 0, 0, 0
+        for i in range(n):
+            k = int(ks[i])
+            lead = T >> (total - L - k)                      # the first L + k bits of the target
+            new_lag = int(rng.integers(0, 2))
+            if lead - new_lag < (X << k):                    # the number never goes down (and never below zero)
+                new_lag = 0
+            v = lead - new_lag - (X << k)
+            assert 0 <= v < (2 << k)
+            vs[i] = v
+            X, L, lag = lead - new_lag, L + k, new_lag
+        out = np.zeros(((L + 31) // 32 + 2) * 4, dtype=np.uint8)
+        ov = C.c_int(0)
+        bits = sim.lib.sim_carry_writer(vs.ctypes.data, ks.ctypes.data, n, out.ctypes.data, out.size, C.byref(ov))
+        assert bits == L and ov.value == 0
+        want = np.zeros(out.size * 8, dtype=np.uint8)
+        if L:
+            want[:L] = [int(c) for c in format(X, "0%db" % L)]
+        assert np.array_equal(np.unpackbits(out)[:((L + 31) // 32) * 32], want[:((L + 31) // 32) * 32]), trial
