@@ -87,6 +87,8 @@ class Sim:
         L.sim_dega_decode_batch.restype = C.c_int
         L.sim_dega_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_check_narrow_w.restype = C.c_uint64
+        L.sim_check_narrow_w.argtypes = [C.c_uint64, C.c_uint64]
         L.sim_dense_reader.restype = C.c_uint32
         L.sim_dense_reader.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.sim_carry_writer.restype = C.c_uint64

@@ -57,6 +57,45 @@ uint64_t sim_csv_encode(const uint32_t *values, uint64_t n, uint32_t column, cha
   return pos;
 }
 
+// The two forms of the encoder's interval update side by side: the top-aligned (a0, LO) pair of narrow_fast() and the one-register
+// form of narrow_w(), on random windows, increments and ranges (pending carries included: lo + dlo may leave the window).  Returns the
+// number of disagreements in the doublings, the new range, the new window or the outgoing bits.
+uint64_t sim_check_narrow_w(uint64_t trials, uint64_t seed)
+{
+  uint64_t bad = 0, x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return x;
+  };
+  for (uint64_t t = 0; t < trials; t++)
+  {
+    const uint32_t lo16 = (uint32_t)rnd() & 0xFFFFu;
+    uint32_t r1 = 1 + (uint32_t)(rnd() % 65536);
+    uint32_t dlo = (uint32_t)(rnd() % 65536);
+    if (t % 4 == 1)
+      r1 = 1 + (uint32_t)(rnd() % 8);          // narrow intervals: many doublings
+    if (t % 4 == 2)
+      dlo = 0x8000u - (lo16 & 0x7FFFu) - (uint32_t)(rnd() % 4);   // around the midpoint: E3 runs
+    dc::BacEncoder a, b;
+    a.init();
+    b.init();
+    a.LO = lo16 << 16;
+    uint32_t kg1 = 0;
+    a.narrow_fast(dlo & 0xFFFFu, r1, kg1);
+    const uint32_t n = kg1 - 1;
+    uint32_t W = dc::BacEncoder::to_w(lo16 << 16), qs = 0;
+    b.narrow_w(W, dlo & 0xFFFFu, r1, qs);
+    const uint32_t n_w = 15u - qs;
+    bool ok = n == n_w && a.rng == b.rng && a.LO == dc::BacEncoder::from_w(W);
+    if (ok && n <= 14)
+      ok = a.a0 == (W >> 17);
+    bad += ok ? 0 : 1;
+  }
+  return bad;
+}
+
 // DenseReader on its own: the stream of `nbits` bits that starts `byte_off` bytes into buf (an allocation of buf_bytes,
 // a multiple of 4); after every step the 32 bits at the current position are recorded, then the position moves on by steps[i]
 // (<= 32).  Returns the position (bits consumed, counted past the end too).

@@ -233,6 +233,12 @@ def test_csv_field_conversion_matches_strtof(sim, oracle):
     assert n_fast > 5000
 
 
+def test_one_register_interval_update_agrees_with_the_top_aligned_one(sim):
+    """BacEncoder::narrow_w against BacEncoder::narrow_fast on 20 M random (window, increment, range) triples: same number
+    of doublings, same new range and window, same outgoing bits (carry included)."""
+    assert sim.lib.sim_check_narrow_w(20_000_000, 1) == 0
+
+
 def test_dense_reader_matches_a_plain_bit_string(sim):
     """The arithmetic decoder's reader (bitio.cuh: DenseReader): every byte phase, stream ends anywhere in a word, bits
     past the end read as zero, the stream that follows in the payload is never seen."""
