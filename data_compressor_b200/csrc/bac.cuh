@@ -470,8 +470,9 @@ struct BacEncoder
     LO = LO0 << n;
   }
 
-  // Same without the capacity test, for the unrolled groups: kg1 counts n + 1 per symbol and the CALLER checks after
-  // the group that the total stayed within a0 (else it redoes the group with narrow()).
+  // Same without the capacity test: kg1 counts n + 1 per symbol and the caller checks afterwards that the total stayed
+  // within a0.  This was the form of the unrolled groups until narrow_w() below replaced it there; it stays as the
+  // plain statement of the step that narrow_w() is tested against (tests/host_sim: sim_check_narrow_w).
   __device__ __forceinline__ void narrow_fast(uint32_t dlo, uint32_t r1, uint32_t &kg1)
   {
     const uint64_t x = (((uint64_t)a0 << 32) | LO) + ((uint64_t)dlo << 16);

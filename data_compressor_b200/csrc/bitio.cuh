@@ -207,19 +207,6 @@ struct BitReader
     }
   }
 
-  // Same with the word requested one refill ahead (`pre`, set by prime()): the load has a whole refill interval to
-  // arrive instead of stalling its consumer.  A reader uses either refill() or prime()/refill_pre(), never both.
-  __device__ __forceinline__ void prime(uint32_t &pre) { pre = fetch32(); }
-  __device__ __forceinline__ void refill_pre(uint32_t &pre)
-  {
-    if (wn <= 32)
-    {
-      win |= (uint64_t)pre << (32 - wn);
-      wn += 32;
-      pre = fetch32();
-    }
-  }
-
   __device__ __forceinline__ uint64_t avail() const { return pos < nbits ? nbits - pos : 0; }
   __device__ __forceinline__ bool eof() const { return pos >= nbits; }
 
